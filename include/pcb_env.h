@@ -1,0 +1,181 @@
+/* pcb_env.h -- C ABI of libpcbgpu: batched RL-PCB placement environments on B200.
+ *
+ * This is the drop-in boundary for the reset/step hot path of
+ * PBozmarov/RL-Environment-for-Component-Placement.  The reference exposes the
+ * path as a Python gym-0.22 class per variant:
+ *
+ *   environment/dummy_env_square.py:37-153             (square)
+ *   environment/dummy_env_rectangular.py:152-432       (rectangle)
+ *   environment/dummy_env_rectangular_pin.py:396-1710  (rectangle_pin)
+ *   environment/dummy_env_rectangular_pin_spatial.py:396-1661 (rectangle_spatial_pin)
+ *
+ * and registers it with the PPO loop through create_env(env_config)
+ * (utils/agent/utils.py:394-418).  Each entry point below cites the reference
+ * interface it replaces.  Conventions: every function returns 0 on success and
+ * a negative pcb_status on error; the message is available from
+ * pcb_last_error() (thread-local).  No exception crosses the ABI.  A handle owns
+ * all of its device buffers, belongs to one GPU, and is not thread-safe.
+ * reset/step are asynchronous on the caller's stream (a CUstream / cudaStream_t
+ * passed as void*; NULL = legacy default stream) and never synchronise.
+ */
+#ifndef PCB_ENV_H_
+#define PCB_ENV_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCB_ABI_VERSION 1
+
+typedef enum {
+  PCB_OK = 0,
+  PCB_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
+  PCB_ERR_CUDA = -2,      /* CUDA runtime error (message has the detail) */
+  PCB_ERR_STATE = -3,     /* call order (e.g. step before instances uploaded) */
+  PCB_ERR_NOMEM = -4
+} pcb_status;
+
+typedef enum {
+  PCB_KIND_SQUARE = 0,        /* dummy_env_square.py */
+  PCB_KIND_RECT = 1,          /* dummy_env_rectangular.py */
+  PCB_KIND_PIN = 2,           /* dummy_env_rectangular_pin.py */
+  PCB_KIND_PIN_SPATIAL = 3    /* dummy_env_rectangular_pin_spatial.py */
+} pcb_kind;
+
+typedef enum { PCB_REWARD_CENTROID = 0, PCB_REWARD_BEAM = 1, PCB_REWARD_BOTH = 2 } pcb_reward_type;
+typedef enum { PCB_ACTION_TUPLE = 0, PCB_ACTION_FLAT = 1 } pcb_action_format;
+
+/* Constructor arguments of DummyPlacementEnv plus the host-evaluated float64
+ * constants of find_reward (dummy_env_rectangular_pin.py:832-909).  The host
+ * side evaluates the constants with the reference's own expression order and
+ * passes them in, so the device never re-derives them. */
+typedef struct pcb_config {
+  int32_t abi_version;          /* PCB_ABI_VERSION */
+  int32_t kind;                 /* pcb_kind */
+  int32_t height, width;        /* grid, 1..64 each */
+  int32_t component_n;          /* square only (dummy_env_square.py:37) */
+  int32_t max_num_components;   /* C: rows of all_components_feature */
+  int32_t max_component_h, max_component_w; /* P = h*w rows per component (pin:481) */
+  int32_t max_num_nets;         /* K = max_num_nets + 1 channels (spatial) */
+  int32_t max_pins;             /* capacity of the per-instance pin table */
+  int32_t reward_type;          /* pcb_reward_type */
+  int32_t reward_beam_width;    /* >= 1 */
+  int32_t norm_uses_fma;        /* 1: ||d|| = sqrt(fma(dy,dy,dx*dx)) like numpy+OpenBLAS ddot */
+  int32_t autoreset;            /* 1: finished envs restart on their next bank slot */
+  int32_t obs_ring;             /* R >= 1 observation slices [R, N, ...] */
+  int32_t reserved0;
+  double weight_wirelength, weight_num_intersections;     /* pin:414-415 */
+  double wirelength_norm;       /* H + W (pin:879) */
+  double intersections_norm;    /* min(avg area pins, avg net pins) (pin:883-896) */
+  double penalty_reward;        /* not-all-placed reward (pin:899-905) */
+  double penalty_wirelength;    /* info value in that case (pin:908) */
+  double penalty_intersections; /* info value in that case (pin:907) */
+} pcb_config_t;
+
+/* Host-side instance bank (struct of arrays), the exchange format of
+ * what reset() draws in the reference
+ * (generate_instances, pin:1006-1035).  Pins are in env.pins (net-major) order. */
+typedef struct pcb_instance_bank {
+  int64_t count;             /* number of instances */
+  const int32_t* n_comp;     /* [count] */
+  const uint8_t* comp_h;     /* [count, max_num_components] */
+  const uint8_t* comp_w;     /* [count, max_num_components] */
+  const int32_t* n_pins;     /* [count]            (pin kinds; may be NULL otherwise) */
+  const int32_t* n_nets;     /* [count] */
+  const uint8_t* pin_comp;   /* [count, max_pins] component_id */
+  const uint8_t* pin_rx;     /* [count, max_pins] relative_x (un-rotated) */
+  const uint8_t* pin_ry;     /* [count, max_pins] relative_y */
+  const uint8_t* pin_net;    /* [count, max_pins] net_id */
+  const uint16_t* pin_id;    /* [count, max_pins] feature-row id (pin:1256-1258) */
+} pcb_instance_bank_t;
+
+typedef struct pcb_env pcb_env_t;
+
+/* DLPack v0.8 subset (the standard, ABI-stable layout of dlpack.h). */
+#ifndef DLPACK_DLPACK_H_
+typedef enum { kDLCPU = 1, kDLCUDA = 2 } DLDeviceType;
+typedef struct { int32_t device_type; int32_t device_id; } DLDevice;
+typedef enum { kDLInt = 0U, kDLUInt = 1U, kDLFloat = 2U } DLDataTypeCode;
+typedef struct { uint8_t code; uint8_t bits; uint16_t lanes; } DLDataType;
+typedef struct {
+  void* data; DLDevice device; int32_t ndim; DLDataType dtype;
+  int64_t* shape; int64_t* strides; uint64_t byte_offset;
+} DLTensor;
+typedef struct DLManagedTensor {
+  DLTensor dl_tensor; void* manager_ctx; void (*deleter)(struct DLManagedTensor* self);
+} DLManagedTensor;
+#endif
+
+/* DummyPlacementEnv.__init__ (square:37, rect:152, pin:396, spatial:396) for
+ * num_envs independent environments on CUDA device `device`. */
+int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** out);
+int pcb_destroy(pcb_env_t* env);
+
+/* Replaces the RNG draw of generate_instances (rect:253-273, pin:1006-1035):
+ * the instances reset() hands out.  Slot of env i, episode e = (i + e*N) % count. */
+int pcb_upload_instances(pcb_env_t* env, const pcb_instance_bank_t* host_bank);
+
+/* Fills the bank with `count` instances drawn on the host by the library's own
+ * generator (same distributions as pin:977-1264 / rect:253-273, counter-based
+ * RNG instead of the global Mersenne-Twister streams).  `gen` carries the
+ * ranges: {min_component_w, max_component_w, min_component_h, max_component_h,
+ * min_num_components, max_num_components, min_num_nets, max_num_nets,
+ * min_num_pins_per_net, max_num_pins_per_net, net_distribution, pin_spread}. */
+int pcb_generate_instances(pcb_env_t* env, const int32_t gen[12], uint64_t seed, int64_t count);
+
+/* DummyPlacementEnv.reset() (square:74, rect:310, pin:1544, spatial:1487) for
+ * every env (d_reset_mask == NULL: episode 0 of each env, statistics cleared)
+ * or for the envs whose mask byte is non-zero (they advance to their next
+ * bank slot).  Writes the initial observation into the current slice. */
+int pcb_reset(pcb_env_t* env, const uint8_t* d_reset_mask, void* stream);
+
+/* DummyPlacementEnv.step(action) (square:115, rect:353, pin:1599, spatial:1551)
+ * for all envs.  d_actions: device int32, [N,2] (square) / [N,3] (o,x,y) when
+ * PCB_ACTION_TUPLE, [N] flat index when PCB_ACTION_FLAT (the decoding of
+ * FlatteningActionWrapper*, env_wrappers.py:80-98, wrapper_square.py:54-69).
+ * Advances the observation ring by one slice and writes obs/reward/done/info. */
+int pcb_step(pcb_env_t* env, const int32_t* d_actions, int action_format, void* stream);
+
+/* The random policy of agent/random/random_policy_*.py:11-58 (uniform over the
+ * valid entries of action_mask) evaluated on device for every env.  Counter-based:
+ * (seed, env index, step counter).  d_actions as for pcb_step / PCB_ACTION_TUPLE. */
+int pcb_sample_random_actions(pcb_env_t* env, uint64_t seed, int32_t* d_actions, void* stream);
+
+/* step() through HOST buffers: copies h_actions (ideally pinned) to the device,
+ * steps, copies reward[N] (f64) and done[N] (u8) back and waits for them.
+ * This is the call the end-to-end benchmark times. */
+int pcb_step_host(pcb_env_t* env, const int32_t* h_actions, int action_format,
+                  double* h_reward, uint8_t* h_done, void* stream);
+
+/* Observation / result tensors as non-owning DLPack views, valid until
+ * pcb_destroy.  Keys: the reference's observation keys (grid, action_mask,
+ * all_components_feature, component_mask, placement_mask, all_pins_num_feature,
+ * all_pins_cat_feature, pin_grid, component_grid) with shape [R, N, ...], and
+ * reward, done, wirelength, num_intersections, episode_return, episode_length
+ * with shape [N].  The deleter frees only the small manager struct. */
+int pcb_get_tensor(pcb_env_t* env, const char* key, DLManagedTensor** out);
+
+/* Index of the ring slice the last reset/step wrote. */
+int pcb_current_slice(pcb_env_t* env);
+
+/* Episode statistics accumulated on device since the last clear:
+ * out = {episodes, sum_return, sum_length, sum_wirelength, sum_intersections,
+ *        steps, 0, 0}.  Synchronises `stream`. */
+int pcb_episode_stats(pcb_env_t* env, double out[8], int reset_counters, void* stream);
+
+/* Copies the compact per-env state (occupancy bitboard rows, little-endian
+ * 64-bit words, [N, 64]) to the host -- for tests and checkpointing. */
+int pcb_get_occupancy(pcb_env_t* env, uint64_t* h_rows, void* stream);
+
+/* Number of kernels this handle has launched so far (bench: gpu_launches). */
+int64_t pcb_launch_count(pcb_env_t* env);
+
+const char* pcb_last_error(void);
+int pcb_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCB_ENV_H_ */

@@ -1,0 +1,106 @@
+"""ctypes binding of libpcbgpu.so (include/pcb_env.h).  No fallback: a missing
+library or symbol raises ImportError/RuntimeError with the build command."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpcbgpu.so")
+ABI_VERSION = 1
+
+SYMBOLS = (
+    "pcb_create", "pcb_destroy", "pcb_upload_instances", "pcb_generate_instances", "pcb_reset",
+    "pcb_step", "pcb_sample_random_actions", "pcb_step_host", "pcb_get_tensor",
+    "pcb_current_slice", "pcb_episode_stats", "pcb_get_occupancy", "pcb_launch_count",
+    "pcb_last_error", "pcb_abi_version",
+)
+
+
+class PcbConfig(ctypes.Structure):
+    _fields_ = [
+        ("abi_version", ctypes.c_int32), ("kind", ctypes.c_int32),
+        ("height", ctypes.c_int32), ("width", ctypes.c_int32),
+        ("component_n", ctypes.c_int32), ("max_num_components", ctypes.c_int32),
+        ("max_component_h", ctypes.c_int32), ("max_component_w", ctypes.c_int32),
+        ("max_num_nets", ctypes.c_int32), ("max_pins", ctypes.c_int32),
+        ("reward_type", ctypes.c_int32), ("reward_beam_width", ctypes.c_int32),
+        ("norm_uses_fma", ctypes.c_int32), ("autoreset", ctypes.c_int32),
+        ("obs_ring", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("weight_wirelength", ctypes.c_double), ("weight_num_intersections", ctypes.c_double),
+        ("wirelength_norm", ctypes.c_double), ("intersections_norm", ctypes.c_double),
+        ("penalty_reward", ctypes.c_double), ("penalty_wirelength", ctypes.c_double),
+        ("penalty_intersections", ctypes.c_double),
+    ]
+
+
+class PcbInstanceBank(ctypes.Structure):
+    _fields_ = [
+        ("count", ctypes.c_int64),
+        ("n_comp", ctypes.c_void_p), ("comp_h", ctypes.c_void_p), ("comp_w", ctypes.c_void_p),
+        ("n_pins", ctypes.c_void_p), ("n_nets", ctypes.c_void_p),
+        ("pin_comp", ctypes.c_void_p), ("pin_rx", ctypes.c_void_p), ("pin_ry", ctypes.c_void_p),
+        ("pin_net", ctypes.c_void_p), ("pin_id", ctypes.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """Loads libpcbgpu.so once; raises with the build hint when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (nvcc, sm_100a).  pcbgpu has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name in SYMBOLS:
+        if not hasattr(lib, name):
+            raise ImportError(f"{LIB_PATH} does not export {name}; rebuild the library")
+    vp, i32, i64, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64
+    lib.pcb_create.argtypes = [ctypes.POINTER(PcbConfig), i32, i32, ctypes.POINTER(vp)]
+    lib.pcb_destroy.argtypes = [vp]
+    lib.pcb_upload_instances.argtypes = [vp, ctypes.POINTER(PcbInstanceBank)]
+    lib.pcb_generate_instances.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), u64, i64]
+    lib.pcb_reset.argtypes = [vp, vp, vp]
+    lib.pcb_step.argtypes = [vp, vp, i32, vp]
+    lib.pcb_sample_random_actions.argtypes = [vp, u64, vp, vp]
+    lib.pcb_step_host.argtypes = [vp, vp, i32, vp, vp, vp]
+    lib.pcb_get_tensor.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
+    lib.pcb_current_slice.argtypes = [vp]
+    lib.pcb_episode_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_double), i32, vp]
+    lib.pcb_get_occupancy.argtypes = [vp, vp, vp]
+    lib.pcb_launch_count.argtypes = [vp]
+    lib.pcb_launch_count.restype = i64
+    lib.pcb_last_error.restype = ctypes.c_char_p
+    lib.pcb_abi_version.restype = i32
+    if lib.pcb_abi_version() != ABI_VERSION:
+        raise ImportError(f"libpcbgpu ABI {lib.pcb_abi_version()} != {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+class PcbError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc < 0:
+        msg = load().pcb_last_error()
+        raise PcbError(f"libpcbgpu error {rc}: {msg.decode() if msg else '?'}")
+    return rc
+
+
+_PyCapsule_New = ctypes.pythonapi.PyCapsule_New
+_PyCapsule_New.restype = ctypes.py_object
+_PyCapsule_New.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
+
+
+def tensor(handle, key):
+    """pcb_get_tensor -> torch tensor sharing the library's device memory."""
+    import torch.utils.dlpack
+
+    out = ctypes.c_void_p()
+    check(load().pcb_get_tensor(handle, key.encode(), ctypes.byref(out)))
+    return torch.utils.dlpack.from_dlpack(_PyCapsule_New(out, b"dltensor", None))

@@ -1,0 +1,575 @@
+// pcb_api.cu -- host side of libpcbgpu: the C ABI of include/pcb_env.h.
+//
+// Owns the device buffers of one handle (state, instance bank, observation ring),
+// packs host instances into the device record format, and launches the kernels of
+// pcb_kernels.cuh.  No CPU implementation of the environment lives here: without a
+// CUDA device every compute entry point fails with PCB_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pcb_env.h"
+#include "pcb_gen.h"
+#include "pcb_kernels.cuh"
+
+using namespace pcb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(expr)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (expr);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return fail(PCB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                  \
+  } while (0)
+
+inline int align16(int v) { return (v + 15) & ~15; }
+
+struct TensorDesc {
+  const char* key;
+  void** ptr;
+  int code, bits;
+  std::vector<int64_t> shape;  // full shape, [R, N, ...] or [N]
+  bool ringed;
+};
+
+}  // namespace
+
+struct pcb_env {
+  pcb_config_t cfg;
+  Dims d;
+  int device, n_envs, ring, slice;
+  bool wide;  // true: 64-bit rows, two rows per lane
+  uint64_t step_no;
+  int64_t launches;
+  size_t smem_bytes;
+  // device buffers
+  uint8_t* state;
+  uint8_t* bank;
+  uint32_t bank_count;
+  Out base;  // slice 0 pointers
+  double* stats;
+  int32_t* d_actions;  // staging for pcb_step_host
+  std::vector<TensorDesc> tensors;
+  std::vector<void*> allocs;
+};
+
+namespace {
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+Out slice_ptrs(const pcb_env* e, int slice) {
+  const Dims& d = e->d;
+  const size_t N = (size_t)e->n_envs, s = (size_t)slice;
+  Out o = e->base;
+  if (o.grid) o.grid += s * N * d.grid_b;
+  if (o.mask) o.mask += s * N * d.mask_b;
+  if (o.feat) o.feat += s * N * d.feat_n;
+  if (o.comp_mask) o.comp_mask += s * N * d.C;
+  if (o.place_mask) o.place_mask += s * N * d.C;
+  if (o.pnum) o.pnum += s * N * d.pnum_n;
+  if (o.pcat) o.pcat += s * N * d.pcat_n;
+  if (o.pgrid) o.pgrid += s * N * d.pgrid_b;
+  if (o.cgrid) o.cgrid += s * N * d.cgrid_b;
+  return o;
+}
+
+Params make_params(const pcb_env* e) {
+  Params p;
+  memset(&p, 0, sizeof p);
+  p.d = e->d;
+  p.out = slice_ptrs(e, e->slice);
+  p.state = e->state;
+  p.bank = e->bank;
+  p.bank_count = e->bank_count;
+  p.n_envs = e->n_envs;
+  p.stats = e->stats;
+  p.step_no = e->step_no;
+  return p;
+}
+
+enum KernelId { K_STEP, K_TERM, K_RESET, K_SAMPLE };
+
+int launch(pcb_env* e, KernelId id, const Params& p, cudaStream_t st) {
+  dim3 grid((e->n_envs + kWarpsPerCta - 1) / kWarpsPerCta), block(kWarpsPerCta * 32);
+  size_t sm = id == K_SAMPLE ? 0 : e->smem_bytes;
+  if (e->wide) {
+    switch (id) {
+      case K_STEP: step_kernel<2, uint64_t><<<grid, block, sm, st>>>(p); break;
+      case K_TERM: terminal_kernel<2, uint64_t><<<grid, block, sm, st>>>(p); break;
+      case K_RESET: reset_kernel<2, uint64_t><<<grid, block, sm, st>>>(p); break;
+      case K_SAMPLE: sample_kernel<2, uint64_t><<<grid, block, sm, st>>>(p); break;
+    }
+  } else {
+    switch (id) {
+      case K_STEP: step_kernel<1, uint32_t><<<grid, block, sm, st>>>(p); break;
+      case K_TERM: terminal_kernel<1, uint32_t><<<grid, block, sm, st>>>(p); break;
+      case K_RESET: reset_kernel<1, uint32_t><<<grid, block, sm, st>>>(p); break;
+      case K_SAMPLE: sample_kernel<1, uint32_t><<<grid, block, sm, st>>>(p); break;
+    }
+  }
+  CU(cudaGetLastError());
+  e->launches += 1;
+  return 0;
+}
+
+template <typename P>
+int dev_alloc(pcb_env* e, P** out, size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 16;
+  cudaError_t err = cudaMalloc(&p, bytes);
+  if (err != cudaSuccess)
+    return fail(err == cudaErrorMemoryAllocation ? PCB_ERR_NOMEM : PCB_ERR_CUDA,
+                "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(err));
+  CU(cudaMemset(p, 0, bytes));
+  e->allocs.push_back(p);
+  *out = reinterpret_cast<P*>(p);
+  return 0;
+}
+
+int check_config(const pcb_config_t* c) {
+  if (!c) return fail(PCB_ERR_INVALID, "config is NULL");
+  if (c->abi_version != PCB_ABI_VERSION)
+    return fail(PCB_ERR_INVALID, "ABI version %d, library is %d", c->abi_version, PCB_ABI_VERSION);
+  if (c->kind < 0 || c->kind > 3) return fail(PCB_ERR_INVALID, "unknown kind %d", c->kind);
+  if (c->height < 1 || c->width < 1 || c->height > kMaxGrid || c->width > kMaxGrid)
+    return fail(PCB_ERR_INVALID, "grid %dx%d outside 1..%d", c->height, c->width, kMaxGrid);
+  if (c->obs_ring < 1) return fail(PCB_ERR_INVALID, "obs_ring must be >= 1");
+  if (c->kind == PCB_KIND_SQUARE) {
+    if (c->component_n < 1 || c->component_n > c->height || c->component_n > c->width)
+      return fail(PCB_ERR_INVALID, "component_n %d does not fit the grid", c->component_n);
+    return 0;
+  }
+  if (c->max_num_components < 1 || c->max_num_components > kMaxComps)
+    return fail(PCB_ERR_INVALID, "max_num_components %d outside 1..%d", c->max_num_components,
+                kMaxComps);
+  int big = std::max(c->max_component_h, c->max_component_w);
+  if (c->max_component_h < 1 || c->max_component_w < 1 || big > std::min(c->height, c->width) ||
+      big > 32)
+    return fail(PCB_ERR_INVALID, "component size %dx%d must fit the grid in both orientations",
+                c->max_component_h, c->max_component_w);
+  if (c->kind >= PCB_KIND_PIN) {
+    if (c->max_num_nets < 1 || c->max_num_nets >= kMaxNets)
+      return fail(PCB_ERR_INVALID, "max_num_nets %d outside 1..%d", c->max_num_nets, kMaxNets - 1);
+    if (c->max_pins < 1 || c->max_pins > kMaxPins)
+      return fail(PCB_ERR_INVALID, "max_pins %d outside 1..%d", c->max_pins, kMaxPins);
+    if (c->max_component_h * c->max_component_w > 255)
+      return fail(PCB_ERR_INVALID, "more than 255 pins per component");
+    if (c->reward_type < 0 || c->reward_type > 2)
+      return fail(PCB_ERR_INVALID, "unknown reward_type %d", c->reward_type);
+    if (c->reward_type != PCB_REWARD_CENTROID &&
+        (c->reward_beam_width < 1 || c->reward_beam_width > kMaxBeamWidth))
+      return fail(PCB_ERR_INVALID, "reward_beam_width %d outside 1..%d", c->reward_beam_width,
+                  kMaxBeamWidth);
+  }
+  return 0;
+}
+
+void fill_dims(const pcb_config_t& c, bool wide, Dims& d) {
+  memset(&d, 0, sizeof d);
+  d.kind = c.kind; d.H = c.height; d.W = c.width;
+  d.O = c.kind == 0 ? 1 : (c.kind == 1 ? 2 : 4);
+  d.sq_n = c.component_n;
+  if (c.kind != 0) {
+    d.C = c.max_num_components; d.mh = c.max_component_h; d.mw = c.max_component_w;
+    d.P = d.mh * d.mw;
+    d.F = c.kind == 3 ? 5 + d.P : 5;
+  }
+  if (c.kind >= 2) { d.K = c.max_num_nets + 1; d.max_pins = c.max_pins; }
+  d.reward_type = c.reward_type; d.beam_width = c.reward_beam_width;
+  d.norm_fma = c.norm_uses_fma; d.autoreset = c.autoreset;
+  const int word = wide ? 8 : 4, rows = wide ? 64 : 32;
+  d.st_comps = 32;
+  d.st_pins = d.st_comps + align16(d.C * 4);
+  d.st_occ = d.st_pins + align16(d.max_pins * 8);
+  d.st_stride = align16(d.st_occ + rows * word);
+  d.rec_comps = 16;
+  d.rec_pins = d.rec_comps + align16(d.C * 4);
+  d.rec_stride = d.rec_pins + align16(d.max_pins * 8);
+  d.grid_b = d.H * d.W;
+  d.mask_b = d.O * d.H * d.W;
+  d.feat_n = d.C * d.F;
+  if (c.kind == 2) { d.pnum_n = d.C * d.P * 4; d.pcat_n = d.C * d.P; }
+  if (c.kind == 3) {
+    d.pnum_n = (d.C * d.P + 1) * 4; d.pcat_n = (d.C * d.P + 1) * 2;
+    d.pgrid_b = d.H * d.W * d.K; d.cgrid_b = d.C * d.mh * d.mw * d.K;
+  }
+  int stage = 16;
+  stage = std::max(stage, (d.pnum_n + d.pcat_n) * 2);
+  if (c.kind == 3) stage = std::max({stage, d.feat_n * 4, d.pgrid_b, d.cgrid_b});
+  d.sm_mrow = d.st_stride;
+  d.sm_stage = d.sm_mrow + 2 * rows * word;
+  d.sm_scr = d.sm_stage + align16(stage) + 16;
+  int scr = c.kind >= 2 ? route_scratch_bytes(d.max_pins, d.K) : 0;
+  d.sm_stride = align16(d.sm_scr + scr);
+  d.ww = c.weight_wirelength; d.wi = c.weight_num_intersections;
+  d.wl_norm = c.wirelength_norm; d.ni_norm = c.intersections_norm;
+  d.pen_reward = c.penalty_reward; d.pen_wl = c.penalty_wirelength; d.pen_ni = c.penalty_intersections;
+}
+
+void dl_deleter(DLManagedTensor* self) {
+  if (!self) return;
+  free(self->dl_tensor.shape);
+  free(self);
+}
+
+int pack_and_upload(pcb_env* e, const pcb_instance_bank_t* b) {
+  const Dims& d = e->d;
+  if (d.kind == 0) return fail(PCB_ERR_INVALID, "the square env has no instances");
+  if (!b || b->count < 1 || !b->n_comp || !b->comp_h || !b->comp_w)
+    return fail(PCB_ERR_INVALID, "instance bank is empty or has NULL arrays");
+  if (d.kind >= 2 && (!b->n_pins || !b->n_nets || !b->pin_comp || !b->pin_rx || !b->pin_ry ||
+                      !b->pin_net || !b->pin_id))
+    return fail(PCB_ERR_INVALID, "pin arrays missing in the instance bank");
+  if (b->count > 0x7fffffffLL) return fail(PCB_ERR_INVALID, "too many instances");
+  const size_t cnt = (size_t)b->count;
+  std::vector<uint8_t> host(cnt * d.rec_stride, 0);
+  std::vector<int> last(kMaxComps * 256);
+  for (size_t i = 0; i < cnt; ++i) {
+    uint8_t* rec = host.data() + i * d.rec_stride;
+    EnvHdr* h = reinterpret_cast<EnvHdr*>(rec);
+    int nc = b->n_comp[i];
+    if (nc < 1 || nc > d.C) return fail(PCB_ERR_INVALID, "instance %zu: n_comp %d outside 1..%d", i, nc, d.C);
+    h->n_comp = (uint8_t)nc;
+    CompRec* comps = reinterpret_cast<CompRec*>(rec + d.rec_comps);
+    for (int c = 0; c < nc; ++c) {
+      int ch = b->comp_h[i * d.C + c], cw = b->comp_w[i * d.C + c];
+      if (ch < 1 || cw < 1 || ch > d.mh || cw > d.mw)
+        return fail(PCB_ERR_INVALID, "instance %zu: component %d is %dx%d, max %dx%d", i, c, ch, cw, d.mh, d.mw);
+      comps[c] = CompRec{(uint8_t)ch, (uint8_t)cw, 0xFF, 0xFF};
+    }
+    if (d.kind < 2) continue;
+    int np = b->n_pins[i], nn = b->n_nets[i];
+    if (np < 0 || np > d.max_pins) return fail(PCB_ERR_INVALID, "instance %zu: n_pins %d outside 0..%d", i, np, d.max_pins);
+    if (nn < 0 || nn >= d.K) return fail(PCB_ERR_INVALID, "instance %zu: n_nets %d outside 0..%d", i, nn, d.K - 1);
+    h->n_pins = (uint16_t)np;
+    h->n_nets = (uint8_t)nn;
+    PinRec* pins = reinterpret_cast<PinRec*>(rec + d.rec_pins);
+    std::fill(last.begin(), last.begin() + (size_t)nc * 256, -1);
+    int rank[kMaxComps] = {0};
+    int prev_net = 0;
+    for (int q = 0; q < np; ++q) {
+      size_t j = i * d.max_pins + q;
+      PinRec r;
+      r.comp = b->pin_comp[j]; r.rx = b->pin_rx[j]; r.ry = b->pin_ry[j]; r.net = b->pin_net[j];
+      r.pin_id = b->pin_id[j]; r.flags = 0; r.rank = 0;
+      if (r.comp >= nc) return fail(PCB_ERR_INVALID, "instance %zu pin %d: component %d >= %d", i, q, r.comp, nc);
+      if (r.rx >= comps[r.comp].h || r.ry >= comps[r.comp].w)
+        return fail(PCB_ERR_INVALID, "instance %zu pin %d: (%d,%d) outside its component", i, q, r.rx, r.ry);
+      if (r.net >= nn || r.net < prev_net)
+        return fail(PCB_ERR_INVALID, "instance %zu pin %d: pins must be net-major, net %d", i, q, r.net);
+      prev_net = r.net;
+      int max_row = d.kind == 3 ? d.C * d.P : d.P;
+      if (r.pin_id >= max_row) return fail(PCB_ERR_INVALID, "instance %zu pin %d: pin_id %d >= %d", i, q, r.pin_id, max_row);
+      r.rank = (uint8_t)rank[r.comp]++;
+      // last writer of a (component, pin_id) feature row wins (update_all_pins_feature,
+      // dummy_env_rectangular_pin.py:1521-1542); the spatial rows are keyed by pin_id alone
+      int key = d.kind == 3 ? 0 : r.comp * 256;
+      if (d.kind == 3) {
+        r.flags = kPinWinner;
+      } else {
+        last[key + r.pin_id] = q;
+      }
+      pins[q] = r;
+    }
+    if (d.kind == 2)
+      for (int q = 0; q < np; ++q)
+        if (last[pins[q].comp * 256 + pins[q].pin_id] == q) pins[q].flags = kPinWinner;
+  }
+  if (e->bank) { cudaFree(e->bank); e->bank = nullptr; }
+  void* p = nullptr;
+  CU(cudaMalloc(&p, host.size()));
+  e->bank = reinterpret_cast<uint8_t*>(p);
+  CU(cudaMemcpy(e->bank, host.data(), host.size(), cudaMemcpyHostToDevice));
+  e->bank_count = (uint32_t)cnt;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pcb_last_error(void) { return g_err.c_str(); }
+int pcb_abi_version(void) { return PCB_ABI_VERSION; }
+
+int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** out) {
+  if (!out) return fail(PCB_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int rc = check_config(cfg);
+  if (rc) return rc;
+  if (num_envs < 1) return fail(PCB_ERR_INVALID, "num_envs must be >= 1");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(PCB_ERR_CUDA, "CUDA device %d not present (%d devices)", device, ndev);
+  CU(cudaSetDevice(device));
+  pcb_env* e = new pcb_env();
+  e->cfg = *cfg;
+  e->device = device; e->n_envs = num_envs; e->ring = cfg->obs_ring; e->slice = 0;
+  e->wide = cfg->height > 32 || cfg->width > 32;
+  e->step_no = 0; e->launches = 0; e->bank = nullptr; e->bank_count = 0;
+  memset(&e->base, 0, sizeof e->base);
+  fill_dims(*cfg, e->wide, e->d);
+  const Dims& d = e->d;
+  e->smem_bytes = (size_t)d.sm_stride * kWarpsPerCta;
+  if (e->smem_bytes > 200 * 1024) {
+    delete e;
+    return fail(PCB_ERR_INVALID, "configuration needs %zu bytes of shared memory per CTA", e->smem_bytes);
+  }
+  auto cleanup = [&](int code) { pcb_destroy(e); return code; };
+#define TRY(x) do { int rc_ = (x); if (rc_) return cleanup(rc_); } while (0)
+  if (e->wide) {
+    TRY(set_smem(step_kernel<2, uint64_t>, e->smem_bytes));
+    TRY(set_smem(terminal_kernel<2, uint64_t>, e->smem_bytes));
+    TRY(set_smem(reset_kernel<2, uint64_t>, e->smem_bytes));
+  } else {
+    TRY(set_smem(step_kernel<1, uint32_t>, e->smem_bytes));
+    TRY(set_smem(terminal_kernel<1, uint32_t>, e->smem_bytes));
+    TRY(set_smem(reset_kernel<1, uint32_t>, e->smem_bytes));
+  }
+  const size_t N = (size_t)num_envs, R = (size_t)e->ring;
+  const int64_t n64 = num_envs, r64 = e->ring;
+  TRY(dev_alloc(e, &e->state, N * d.st_stride));
+  TRY(dev_alloc(e, &e->stats, kStatSlots * 8 * sizeof(double)));
+  TRY(dev_alloc(e, &e->d_actions, N * 3 * sizeof(int32_t)));
+  auto add = [&](const char* key, void** ptr, int code, int bits, std::vector<int64_t> shape, bool ringed) {
+    e->tensors.push_back(TensorDesc{key, ptr, code, bits, std::move(shape), ringed});
+  };
+  TRY(dev_alloc(e, &e->base.grid, R * N * d.grid_b));
+  add("grid", (void**)&e->base.grid, kDLUInt, 8, {r64, n64, d.H, d.W}, true);
+  TRY(dev_alloc(e, &e->base.mask, R * N * d.mask_b));
+  if (d.kind == 0) add("action_mask", (void**)&e->base.mask, kDLUInt, 8, {r64, n64, d.H, d.W}, true);
+  else add("action_mask", (void**)&e->base.mask, kDLUInt, 8, {r64, n64, d.O, d.H, d.W}, true);
+  if (d.kind >= 1) {
+    TRY(dev_alloc(e, &e->base.feat, R * N * d.feat_n * sizeof(float)));
+    add("all_components_feature", (void**)&e->base.feat, kDLFloat, 32, {r64, n64, d.C, d.F}, true);
+    TRY(dev_alloc(e, &e->base.place_mask, R * N * d.C));
+    add("placement_mask", (void**)&e->base.place_mask, kDLUInt, 8, {r64, n64, d.C}, true);
+  }
+  if (d.kind == 1) {
+    TRY(dev_alloc(e, &e->base.comp_mask, R * N * d.C));
+    add("component_mask", (void**)&e->base.comp_mask, kDLUInt, 8, {r64, n64, d.C}, true);
+  }
+  if (d.kind >= 2) {
+    TRY(dev_alloc(e, &e->base.pnum, R * N * d.pnum_n * sizeof(int16_t)));
+    TRY(dev_alloc(e, &e->base.pcat, R * N * d.pcat_n * sizeof(int16_t)));
+    if (d.kind == 2) {
+      add("all_pins_num_feature", (void**)&e->base.pnum, kDLInt, 16, {r64, n64, d.C, d.P, 4}, true);
+      add("all_pins_cat_feature", (void**)&e->base.pcat, kDLInt, 16, {r64, n64, d.C, d.P, 1}, true);
+    } else {
+      add("all_pins_num_feature", (void**)&e->base.pnum, kDLInt, 16, {r64, n64, d.C * d.P + 1, 4}, true);
+      add("all_pins_cat_feature", (void**)&e->base.pcat, kDLInt, 16, {r64, n64, d.C * d.P + 1, 2}, true);
+      TRY(dev_alloc(e, &e->base.pgrid, R * N * d.pgrid_b));
+      add("pin_grid", (void**)&e->base.pgrid, kDLUInt, 8, {r64, n64, d.H, d.W, d.K}, true);
+      TRY(dev_alloc(e, &e->base.cgrid, R * N * d.cgrid_b));
+      add("component_grid", (void**)&e->base.cgrid, kDLUInt, 8, {r64, n64, d.C, d.mh, d.mw, d.K}, true);
+    }
+  }
+  TRY(dev_alloc(e, &e->base.reward, N * sizeof(double)));
+  add("reward", (void**)&e->base.reward, kDLFloat, 64, {n64}, false);
+  TRY(dev_alloc(e, &e->base.done, N));
+  add("done", (void**)&e->base.done, kDLUInt, 8, {n64}, false);
+  TRY(dev_alloc(e, &e->base.wl, N * sizeof(double)));
+  add("wirelength", (void**)&e->base.wl, kDLFloat, 64, {n64}, false);
+  TRY(dev_alloc(e, &e->base.ni, N * sizeof(double)));
+  add("num_intersections", (void**)&e->base.ni, kDLFloat, 64, {n64}, false);
+  TRY(dev_alloc(e, &e->base.ep_return, N * sizeof(double)));
+  add("episode_return", (void**)&e->base.ep_return, kDLFloat, 64, {n64}, false);
+  TRY(dev_alloc(e, &e->base.ep_length, N * sizeof(int32_t)));
+  add("episode_length", (void**)&e->base.ep_length, kDLInt, 32, {n64}, false);
+#undef TRY
+  *out = e;
+  return 0;
+}
+
+int pcb_destroy(pcb_env_t* e) {
+  if (!e) return 0;
+  cudaSetDevice(e->device);
+  for (void* p : e->allocs) cudaFree(p);
+  if (e->bank) cudaFree(e->bank);
+  delete e;
+  return 0;
+}
+
+int pcb_upload_instances(pcb_env_t* e, const pcb_instance_bank_t* host_bank) {
+  if (!e) return fail(PCB_ERR_INVALID, "env is NULL");
+  CU(cudaSetDevice(e->device));
+  return pack_and_upload(e, host_bank);
+}
+
+int pcb_generate_instances(pcb_env_t* e, const int32_t gen[12], uint64_t seed, int64_t count) {
+  if (!e || !gen) return fail(PCB_ERR_INVALID, "NULL argument");
+  if (e->d.kind == 0) return fail(PCB_ERR_INVALID, "the square env has no instances");
+  if (count < 1) return fail(PCB_ERR_INVALID, "count must be >= 1");
+  CU(cudaSetDevice(e->device));
+  GenBank gb;
+  std::string why;
+  if (!generate_bank(gen, e->d.kind, e->d.C, e->d.max_pins, e->d.K - 1, seed, count, gb, why))
+    return fail(PCB_ERR_INVALID, "instance generator: %s", why.c_str());
+  pcb_instance_bank_t b;
+  memset(&b, 0, sizeof b);
+  b.count = count;
+  b.n_comp = gb.n_comp.data(); b.comp_h = gb.comp_h.data(); b.comp_w = gb.comp_w.data();
+  if (e->d.kind >= 2) {
+    b.n_pins = gb.n_pins.data(); b.n_nets = gb.n_nets.data();
+    b.pin_comp = gb.pin_comp.data(); b.pin_rx = gb.pin_rx.data(); b.pin_ry = gb.pin_ry.data();
+    b.pin_net = gb.pin_net.data(); b.pin_id = gb.pin_id.data();
+  }
+  return pack_and_upload(e, &b);
+}
+
+static int ready(pcb_env_t* e) {
+  if (!e) return fail(PCB_ERR_INVALID, "env is NULL");
+  if (e->d.kind != 0 && !e->bank) return fail(PCB_ERR_STATE, "no instances uploaded (pcb_upload_instances / pcb_generate_instances)");
+  return 0;
+}
+
+int pcb_reset(pcb_env_t* e, const uint8_t* d_reset_mask, void* stream) {
+  int rc = ready(e);
+  if (rc) return rc;
+  CU(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!d_reset_mask) {
+    e->slice = 0;
+    e->step_no = 0;
+    CU(cudaMemsetAsync(e->stats, 0, kStatSlots * 8 * sizeof(double), st));
+  }
+  Params p = make_params(e);
+  p.reset_mask = d_reset_mask;
+  p.reset_first = d_reset_mask ? 0 : 1;
+  return launch(e, K_RESET, p, st);
+}
+
+int pcb_step(pcb_env_t* e, const int32_t* d_actions, int action_format, void* stream) {
+  int rc = ready(e);
+  if (rc) return rc;
+  if (!d_actions) return fail(PCB_ERR_INVALID, "d_actions is NULL");
+  if (action_format != PCB_ACTION_TUPLE && action_format != PCB_ACTION_FLAT)
+    return fail(PCB_ERR_INVALID, "unknown action format %d", action_format);
+  CU(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  e->slice = (e->slice + 1) % e->ring;
+  Params p = make_params(e);
+  p.actions = d_actions;
+  p.action_format = action_format;
+  rc = launch(e, K_STEP, p, st);
+  if (rc) return rc;
+  rc = launch(e, K_TERM, p, st);
+  e->step_no += 1;
+  return rc;
+}
+
+int pcb_sample_random_actions(pcb_env_t* e, uint64_t seed, int32_t* d_actions, void* stream) {
+  int rc = ready(e);
+  if (rc) return rc;
+  if (!d_actions) return fail(PCB_ERR_INVALID, "d_actions is NULL");
+  CU(cudaSetDevice(e->device));
+  Params p = make_params(e);
+  p.seed = seed;
+  p.actions_out = d_actions;
+  return launch(e, K_SAMPLE, p, (cudaStream_t)stream);
+}
+
+int pcb_step_host(pcb_env_t* e, const int32_t* h_actions, int action_format, double* h_reward,
+                  uint8_t* h_done, void* stream) {
+  int rc = ready(e);
+  if (rc) return rc;
+  if (!h_actions || !h_reward || !h_done) return fail(PCB_ERR_INVALID, "NULL host buffer");
+  CU(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t per = action_format == PCB_ACTION_FLAT ? 1 : (e->d.kind == 0 ? 2 : 3);
+  CU(cudaMemcpyAsync(e->d_actions, h_actions, (size_t)e->n_envs * per * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  rc = pcb_step(e, e->d_actions, action_format, stream);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h_reward, e->base.reward, (size_t)e->n_envs * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h_done, e->base.done, (size_t)e->n_envs, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int pcb_get_tensor(pcb_env_t* e, const char* key, DLManagedTensor** out) {
+  if (!e || !key || !out) return fail(PCB_ERR_INVALID, "NULL argument");
+  for (const TensorDesc& t : e->tensors) {
+    if (strcmp(t.key, key)) continue;
+    DLManagedTensor* m = (DLManagedTensor*)calloc(1, sizeof(DLManagedTensor));
+    int64_t* shape = (int64_t*)malloc(sizeof(int64_t) * t.shape.size());
+    if (!m || !shape) { free(m); free(shape); return fail(PCB_ERR_NOMEM, "out of host memory"); }
+    for (size_t i = 0; i < t.shape.size(); ++i) shape[i] = t.shape[i];
+    m->dl_tensor.data = *t.ptr;
+    m->dl_tensor.device = DLDevice{kDLCUDA, e->device};
+    m->dl_tensor.ndim = (int32_t)t.shape.size();
+    m->dl_tensor.dtype = DLDataType{(uint8_t)t.code, (uint8_t)t.bits, 1};
+    m->dl_tensor.shape = shape;
+    m->dl_tensor.strides = nullptr;
+    m->dl_tensor.byte_offset = 0;
+    m->manager_ctx = nullptr;
+    m->deleter = dl_deleter;
+    *out = m;
+    return 0;
+  }
+  return fail(PCB_ERR_INVALID, "no tensor named '%s' for this environment kind", key);
+}
+
+int pcb_current_slice(pcb_env_t* e) { return e ? e->slice : fail(PCB_ERR_INVALID, "env is NULL"); }
+
+int pcb_episode_stats(pcb_env_t* e, double out[8], int reset_counters, void* stream) {
+  if (!e || !out) return fail(PCB_ERR_INVALID, "NULL argument");
+  CU(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  double host[kStatSlots * 8];
+  CU(cudaMemcpyAsync(host, e->stats, sizeof host, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  for (int j = 0; j < 8; ++j) out[j] = 0.0;
+  for (int s = 0; s < kStatSlots; ++s)
+    for (int j = 0; j < 8; ++j) out[j] += host[s * 8 + j];
+  out[5] = (double)e->step_no * (double)e->n_envs;
+  if (reset_counters) CU(cudaMemsetAsync(e->stats, 0, sizeof host, st));
+  return 0;
+}
+
+int pcb_get_occupancy(pcb_env_t* e, uint64_t* h_rows, void* stream) {
+  if (!e || !h_rows) return fail(PCB_ERR_INVALID, "NULL argument");
+  CU(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const Dims& d = e->d;
+  std::vector<uint8_t> host((size_t)e->n_envs * d.st_stride);
+  CU(cudaMemcpyAsync(host.data(), e->state, host.size(), cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  for (int i = 0; i < e->n_envs; ++i) {
+    const uint8_t* occ = host.data() + (size_t)i * d.st_stride + d.st_occ;
+    for (int r = 0; r < 64; ++r) {
+      uint64_t v = 0;
+      if (e->wide) v = reinterpret_cast<const uint64_t*>(occ)[r];
+      else if (r < 32) v = reinterpret_cast<const uint32_t*>(occ)[r];
+      h_rows[(size_t)i * 64 + r] = v;
+    }
+  }
+  return 0;
+}
+
+int64_t pcb_launch_count(pcb_env_t* e) { return e ? e->launches : 0; }
+
+}  // extern "C"

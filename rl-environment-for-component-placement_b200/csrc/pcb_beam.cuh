@@ -1,0 +1,258 @@
+// pcb_beam.cuh -- the beam-search route of the reward (route_pins_beam_search,
+// dummy_env_rectangular_pin.py:1425-1460; beam_search :1356-1423; pin_outlier :1326-1339).
+//
+// The reference breaks distance ties at the beam cut-off by the iteration order
+// of a CPython set difference, so this file reproduces Objects/setobject.c's
+// table placement for (int, int) tuples: tuple hash, linear-probe + perturb
+// sequence, growth at 3/5 fill to the next power of two above 4*used, the
+// copy-vs-rebuild choice of set_difference.  The executable specification is
+// oracle/pyset_model.py (checked against real sets in tests/test_pyset_model.py).
+// One lane routes one net (nets are independent); runs on terminal steps only.
+#ifndef PCB_BEAM_CUH_
+#define PCB_BEAM_CUH_
+
+namespace pcb {
+
+constexpr int kTab = 32;  // a set of <= 18 keys never grows past 32 slots
+
+__device__ __forceinline__ uint64_t rotl64(uint64_t v, int s) { return (v << s) | (v >> (64 - s)); }
+
+__device__ __forceinline__ uint64_t py_tuple_hash(int x, int y) {
+  const uint64_t P1 = 11400714785074694791ull, P2 = 14029467366897019727ull,
+                 P5 = 2870177450012600261ull;
+  uint64_t acc = P5;
+  acc += (uint64_t)x * P2; acc = rotl64(acc, 31); acc *= P1;
+  acc += (uint64_t)y * P2; acc = rotl64(acc, 31); acc *= P1;
+  acc += 2ull ^ (P5 ^ 3527539ull);
+  return acc == ~0ull ? 1546275796ull : acc;
+}
+
+struct PyTab {
+  int8_t s[kTab];  // key index or -1 (empty)
+  int mask, used;
+};
+
+__device__ __forceinline__ int tab_free_slot(const int8_t* s, int mask, uint64_t h) {
+  uint64_t perturb = h;
+  int i = (int)(h & (uint64_t)mask);
+  while (true) {
+    if (s[i] < 0) return i;
+    if (i + 9 <= mask) {
+      for (int j = 1; j <= 9; ++j)
+        if (s[i + j] < 0) return i + j;
+    }
+    perturb >>= 5;
+    i = (int)(((uint64_t)i * 5 + 1 + perturb) & (uint64_t)mask);
+  }
+}
+
+__device__ __forceinline__ void tab_clear(PyTab& t, int size) {
+  for (int i = 0; i < kTab; ++i) t.s[i] = -1;
+  t.mask = size - 1;
+  t.used = 0;
+}
+
+// re-insert the live keys of `t` in table order into a table of the first power
+// of two > minused (set_table_resize)
+__device__ __forceinline__ void tab_resize(PyTab& t, int minused, const uint64_t* h) {
+  int size = 8;
+  while (size <= minused) size <<= 1;
+  int8_t old[kTab];
+  int n = 0;
+  for (int i = 0; i <= t.mask; ++i)
+    if (t.s[i] >= 0) old[n++] = t.s[i];
+  tab_clear(t, size);
+  for (int i = 0; i < n; ++i) t.s[tab_free_slot(t.s, t.mask, h[old[i]])] = old[i];
+  t.used = n;
+}
+
+__device__ __forceinline__ void tab_add(PyTab& t, int key, const uint64_t* h) {  // set_add_entry
+  t.s[tab_free_slot(t.s, t.mask, h[key])] = (int8_t)key;
+  t.used += 1;
+  if (t.used * 5 >= t.mask * 3) tab_resize(t, t.used * 4, h);
+}
+
+// iteration order of (targets - seen); returns the number of keys written to out[]
+__device__ __forceinline__ int tab_difference(const PyTab& targets, uint32_t seen,
+                                              const uint64_t* h, int8_t* out) {
+  PyTab r;
+  int n = 0;
+  if ((targets.used >> 2) > __popc(seen)) {
+    // set_copy_and_difference: copy (set_merge into a fresh set), then discard
+    tab_clear(r, 8);
+    if (targets.used * 5 >= r.mask * 3) {
+      int size = 8;
+      while (size <= targets.used * 2) size <<= 1;
+      tab_clear(r, size);
+    }
+    if (r.mask == targets.mask) {
+      for (int i = 0; i <= targets.mask; ++i)
+        if (targets.s[i] >= 0 && !((seen >> targets.s[i]) & 1u)) out[n++] = targets.s[i];
+      return n;
+    }
+    for (int i = 0; i <= targets.mask; ++i)
+      if (targets.s[i] >= 0) r.s[tab_free_slot(r.s, r.mask, h[targets.s[i]])] = targets.s[i];
+    for (int i = 0; i <= r.mask; ++i)
+      if (r.s[i] >= 0 && !((seen >> r.s[i]) & 1u)) out[n++] = r.s[i];
+    return n;
+  }
+  tab_clear(r, 8);
+  for (int i = 0; i <= targets.mask; ++i) {
+    int k = targets.s[i];
+    if (k >= 0 && !((seen >> k) & 1u)) tab_add(r, k, h);
+  }
+  for (int i = 0; i <= r.mask; ++i)
+    if (r.s[i] >= 0) out[n++] = r.s[i];
+  return n;
+}
+
+struct BeamItem {
+  double prio;
+  uint32_t seen;
+  int8_t path[kMaxBeamPoints + 1];  // local point indices after the start point
+};
+
+// lexicographic (priority, path) order of heapq on (float, list-of-tuples) entries
+__device__ __forceinline__ bool beam_less(const BeamItem& a, const BeamItem& b, int len,
+                                          const int16_t* x, const int16_t* y) {
+  if (a.prio != b.prio) return a.prio < b.prio;
+  for (int i = 0; i < len; ++i) {
+    int pa = a.path[i], pb = b.path[i];
+    if (x[pa] != x[pb]) return x[pa] < x[pb];
+    if (y[pa] != y[pb]) return y[pa] < y[pb];
+  }
+  return false;
+}
+
+// Routes every net; fills rs.start[net] and rs.nxt[pin] (global pin indices).
+template <typename T>
+__device__ __noinline__ void beam_paths(const Dims& d, const Env<T>& e, const RouteScratch& rs,
+                                        int lane, int n_nets) {
+  const int bw = d.beam_width;
+  for (int net = lane; net < n_nets; net += 32) {
+    const int lo = rs.net_off[net], m_all = rs.net_off[net + 1] - lo;
+    // pin_outlier: first farthest pin from the centroid
+    int start = 0;
+    {
+      double best = -1.0;
+      const double cx = rs.cx[net], cy = rs.cy[net];
+      for (int i = 0; i < m_all; ++i) {
+        double v = norm2((double)rs.px[lo + i] - cx, (double)rs.py[lo + i] - cy, d.norm_fma);
+        if (v > best) { best = v; start = i; }
+      }
+    }
+    // points = net pins without the start (list.remove keeps the order)
+    int16_t x[kMaxBeamPoints + 1], y[kMaxBeamPoints + 1];
+    uint16_t gid[kMaxBeamPoints + 1];
+    uint64_t h[kMaxBeamPoints + 1];
+    int m = 0;
+    for (int i = 0; i < m_all; ++i) {
+      if (i == start) continue;
+      x[m] = rs.px[lo + i]; y[m] = rs.py[lo + i]; gid[m] = (uint16_t)(lo + i);
+      h[m] = py_tuple_hash(x[m], y[m]);
+      ++m;
+    }
+    const int sx = rs.px[lo + start], sy = rs.py[lo + start];
+    PyTab targets;
+    tab_clear(targets, 8);
+    for (int k = 0; k < m; ++k) tab_add(targets, k, h);
+    const uint32_t all = m >= 32 ? ~0u : ((1u << m) - 1u);
+
+    BeamItem q[kMaxBeamWidth * kMaxBeamWidth], nq[kMaxBeamWidth * kMaxBeamWidth];
+    int qn = 1;
+    q[0].prio = 0.0; q[0].seen = 0u;
+    int best_idx = 0;
+    for (int level = 0; level <= m; ++level) {  // level == number of visited points
+      // order the queue (selection of the min(bw, qn) smallest entries)
+      int order[kMaxBeamWidth];
+      int take = bw < qn ? bw : qn;
+      uint32_t used = 0;
+      for (int t = 0; t < take; ++t) {
+        int bi = -1;
+        for (int i = 0; i < qn; ++i) {
+          if ((used >> i) & 1u) continue;
+          if (bi < 0 || beam_less(q[i], q[bi], level, x, y)) bi = i;
+        }
+        used |= 1u << bi;
+        order[t] = bi;
+      }
+      if (level == m) { best_idx = order[0]; break; }  // first popped complete path wins
+      int nn = 0;
+      for (int t = 0; t < take; ++t) {
+        const BeamItem& it = q[order[t]];
+        const int hx = level ? x[it.path[level - 1]] : sx, hy = level ? y[it.path[level - 1]] : sy;
+        int8_t cand[kMaxBeamPoints + 1];
+        double cd[kMaxBeamPoints + 1];
+        int nc = tab_difference(targets, it.seen, h, cand);
+        for (int i = 0; i < nc; ++i)
+          cd[i] = norm2((double)(hx - x[cand[i]]), (double)(hy - y[cand[i]]), d.norm_fma);
+        // stable insertion sort by distance (sorted(..., key=...))
+        for (int i = 1; i < nc; ++i) {
+          int8_t ck = cand[i]; double dk = cd[i];
+          int j = i - 1;
+          while (j >= 0 && cd[j] > dk) { cand[j + 1] = cand[j]; cd[j + 1] = cd[j]; --j; }
+          cand[j + 1] = ck; cd[j + 1] = dk;
+        }
+        int kids = bw < nc ? bw : nc;
+        for (int i = 0; i < kids; ++i) {
+          BeamItem& c = nq[nn++];
+          c.prio = it.prio + cd[i];
+          c.seen = it.seen | (1u << cand[i]);
+          for (int j = 0; j < level; ++j) c.path[j] = it.path[j];
+          c.path[level] = cand[i];
+        }
+      }
+      for (int i = 0; i < nn; ++i) q[i] = nq[i];
+      qn = nn;
+      (void)all;
+    }
+    // publish the path as a linked list over global pin indices
+    rs.start[net] = (uint16_t)(lo + start);
+    uint16_t prev = (uint16_t)(lo + start);
+    for (int j = 0; j < m; ++j) {
+      uint16_t g = gid[q[best_idx].path[j]];
+      rs.nxt[prev] = g;
+      prev = g;
+    }
+    rs.nxt[prev] = 0xFFFF;
+  }
+  __syncwarp();
+}
+
+// crossings + wirelength of the beam route: segment headed by pin q = (q, nxt[q])
+template <typename T>
+__device__ __forceinline__ void beam_route(const Dims& d, const Env<T>& e, const RouteScratch& rs,
+                                           int lane, int n_pins, int n_nets, int& crossings,
+                                           double& wl) {
+  int cnt = 0;
+  for (int s = 0; s < n_pins; ++s) {
+    const int sn = rs.nxt[s];
+    if (sn == 0xFFFF) continue;
+    const double sx1 = rs.px[s], sy1 = rs.py[s], sx2 = rs.px[sn], sy2 = rs.py[sn];
+    const int snet = e.pins[s].net;
+    for (int t = rs.net_off[snet + 1] + lane; t < n_pins; t += 32) {
+      const int tn = rs.nxt[t];
+      if (tn == 0xFFFF) continue;
+      if (segments_cross(sx1, sy1, sx2, sy2, rs.px[t], rs.py[t], rs.px[tn], rs.py[tn])) ++cnt;
+    }
+  }
+  for (int off = 16; off; off >>= 1) cnt += __shfl_xor_sync(kFull, cnt, off);
+  crossings = cnt;
+  // find_wirelength: nets in order, segments in path order, sequential float64 sum
+  double acc = 0.0;
+  if (lane == 0) {
+    for (int net = 0; net < n_nets; ++net) {
+      int q = rs.start[net];
+      while (rs.nxt[q] != 0xFFFF) {
+        int nx = rs.nxt[q];
+        acc += norm2((double)(rs.px[q] - rs.px[nx]), (double)(rs.py[q] - rs.py[nx]), d.norm_fma);
+        q = nx;
+      }
+    }
+  }
+  wl = __shfl_sync(kFull, acc, 0);
+  __syncwarp();
+}
+
+}  // namespace pcb
+#endif

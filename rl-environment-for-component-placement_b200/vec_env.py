@@ -1,0 +1,191 @@
+"""PcbVecEnv -- the batched, device-resident replacement of the reference's
+``DummyPlacementEnv`` classes (one object = N environments on one B200).
+
+API mirrors gym-0.22 as the reference uses it (``reset() -> obs``,
+``step(a) -> (obs, reward, done, info)``; dummy_env_rectangular_pin.py:1544-1710)
+with a leading batch dimension; every tensor is a torch view (DLPack) of memory
+owned by libpcbgpu, nothing is copied or computed on the host.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import make_spec
+from .instances import InstanceBank
+
+OBS_KEYS = {
+    "square": ("grid", "action_mask"),
+    "rectangle": ("grid", "action_mask", "all_components_feature", "component_mask",
+                  "placement_mask"),
+    "rectangle_pin": ("grid", "action_mask", "all_components_feature", "placement_mask",
+                      "all_pins_num_feature", "all_pins_cat_feature"),
+    "rectangle_spatial_pin": ("grid", "action_mask", "all_components_feature", "placement_mask",
+                              "all_pins_num_feature", "all_pins_cat_feature", "pin_grid",
+                              "component_grid"),
+}
+RESULT_KEYS = ("reward", "done", "wirelength", "num_intersections", "episode_return",
+               "episode_length")
+
+
+class PcbVecEnv:
+    """N independent placement environments stepping in CUDA kernels.
+
+    env_config : dict with the keys of the reference's ``env_config`` JSON blocks
+                 (agent/config/*.json), ``type`` in {square, rectangle,
+                 rectangle_pin, rectangle_spatial_pin} or a model-type alias.
+    instances  : list of instances (oracle ``Instance`` objects / dicts) or an
+                 ``InstanceBank``; default: ``bank_size`` instances from the
+                 library's generator seeded with ``seed``.
+    autoreset  : True  -> a finished env restarts on its next bank slot and the
+                          returned observation is the first of the new episode;
+                 False -> the terminal observation is returned as the reference
+                          returns it and the env stays as it is until ``reset``.
+    """
+
+    def __init__(self, env_config, num_envs, device=0, autoreset=True, obs_ring=1,
+                 instances=None, bank_size=None, seed=0, norm_uses_fma=True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("pcbgpu needs a CUDA device; there is no CPU fallback")
+        self.lib = _lib.load()
+        self.spec = make_spec(env_config, autoreset, obs_ring, norm_uses_fma)
+        self.kind = self.spec.kind
+        self.num_envs = int(num_envs)
+        self.device = torch.device("cuda", int(device))
+        self.autoreset = bool(autoreset)
+        self._h = ctypes.c_void_p()
+        _lib.check(self.lib.pcb_create(ctypes.byref(self.spec.c), int(device), self.num_envs,
+                                       ctypes.byref(self._h)))
+        self._ring = {k: _lib.tensor(self._h, k) for k in OBS_KEYS[self.kind]}
+        self._res = {k: _lib.tensor(self._h, k) for k in RESULT_KEYS}
+        self._actions = torch.zeros((self.num_envs, self.spec.action_width), dtype=torch.int32,
+                                    device=self.device)
+        if self.kind != "square":
+            if instances is not None:
+                self.set_instances(instances)
+            else:
+                self.generate_instances(bank_size or self.num_envs, seed)
+
+    # -- lifecycle -----------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._ring, self._res = {}, {}
+            self.lib.pcb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # -- instances -----------------------------------------------------------
+    def set_instances(self, instances):
+        bank = instances if isinstance(instances, InstanceBank) else InstanceBank.from_list(
+            self.spec, list(instances))
+        s = bank.as_struct()
+        _lib.check(self.lib.pcb_upload_instances(self._h, ctypes.byref(s)))
+        self.bank_size = bank.count
+
+    def generate_instances(self, count, seed=0):
+        arr = (ctypes.c_int32 * 12)(*self.spec.generator_ranges())
+        _lib.check(self.lib.pcb_generate_instances(self._h, arr, ctypes.c_uint64(seed),
+                                                   ctypes.c_int64(count)))
+        self.bank_size = int(count)
+
+    # -- gym surface ---------------------------------------------------------
+    def _obs(self):
+        s = self.lib.pcb_current_slice(self._h)
+        return {k: v[s] for k, v in self._ring.items()}
+
+    def reset(self, mask=None):
+        """reset() of every env (mask None) or of the envs where ``mask`` is set."""
+        ptr = None
+        if mask is not None:
+            mask = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+            ptr = ctypes.c_void_p(mask.data_ptr())
+        _lib.check(self.lib.pcb_reset(self._h, ptr, self._stream()))
+        return self._obs()
+
+    def step_async(self, actions):
+        a = torch.as_tensor(actions, device=self.device)
+        if a.dtype != torch.int32 or not a.is_contiguous():
+            a = a.to(torch.int32).contiguous()
+        if a.dim() == 1:
+            if a.numel() != self.num_envs:
+                raise ValueError("flat actions must have shape [num_envs]")
+            fmt = 1
+        else:
+            if tuple(a.shape) != (self.num_envs, self.spec.action_width):
+                raise ValueError(f"actions must have shape [{self.num_envs}, "
+                                 f"{self.spec.action_width}] or [{self.num_envs}]")
+            fmt = 0
+        self._last_actions = a  # keep alive until the kernels ran
+        _lib.check(self.lib.pcb_step(self._h, ctypes.c_void_p(a.data_ptr()), fmt, self._stream()))
+
+    def step(self, actions):
+        self.step_async(actions)
+        r = self._res
+        info = {k: r[k] for k in ("wirelength", "num_intersections", "episode_return",
+                                  "episode_length")}
+        return self._obs(), r["reward"], r["done"], info
+
+    def sample_random_actions(self, seed=0, out=None):
+        """agent/random/random_policy_*.py on device: uniform over the valid actions."""
+        out = self._actions if out is None else out
+        _lib.check(self.lib.pcb_sample_random_actions(
+            self._h, ctypes.c_uint64(seed), ctypes.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def step_host(self, actions_np, reward_np, done_np):
+        """step() through host buffers (pcb_step_host): H2D actions, D2H reward/done."""
+        fmt = 1 if actions_np.ndim == 1 else 0
+        _lib.check(self.lib.pcb_step_host(
+            self._h, ctypes.c_void_p(actions_np.ctypes.data), fmt,
+            ctypes.c_void_p(reward_np.ctypes.data), ctypes.c_void_p(done_np.ctypes.data),
+            self._stream()))
+
+    # -- views ---------------------------------------------------------------
+    @property
+    def action_mask(self):
+        return self._obs()["action_mask"]
+
+    @property
+    def action_mask_flat(self):
+        """FlatteningActionMaskObservationWrapper*: C-order flatten per env."""
+        return self.action_mask.reshape(self.num_envs, -1)
+
+    def decode_flat_actions(self, a):
+        """FlatteningActionWrapper*.action (env_wrappers.py:80-98, wrapper_square.py:54-69)."""
+        a = torch.as_tensor(a, device=self.device).long()
+        H, W = self.spec.height, self.spec.width
+        if self.kind == "square":
+            return torch.stack((a // W, a % W), 1).int()
+        o, rem = a // (H * W), a % (H * W)
+        return torch.stack((o, rem // W, rem % W), 1).int()
+
+    def occupancy(self):
+        """[N, 64] uint64 bitboard rows (bit j of row r = grid[r, j])."""
+        rows = np.zeros((self.num_envs, 64), np.uint64)
+        _lib.check(self.lib.pcb_get_occupancy(self._h, ctypes.c_void_p(rows.ctypes.data),
+                                              self._stream()))
+        return rows
+
+    def episode_stats(self, reset=False):
+        out = (ctypes.c_double * 8)()
+        _lib.check(self.lib.pcb_episode_stats(self._h, out, 1 if reset else 0, self._stream()))
+        keys = ("episodes", "sum_return", "sum_length", "sum_wirelength", "sum_intersections",
+                "steps")
+        return {k: out[i] for i, k in enumerate(keys)}
+
+    @property
+    def launch_count(self):
+        return int(self.lib.pcb_launch_count(self._h))
+
+    @property
+    def obs_ring_tensors(self):
+        return self._ring

@@ -1,0 +1,53 @@
+"""Parity of the CUDA environments (through the C ABI) with the oracle: the
+parity tests proper.  Run on the B200 box (`pytest -m gpu`)."""
+import pytest
+
+from parity import run_parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["A", "A2", "S_sq"])
+def test_square(name):
+    run_parity(name, range(16), extra_steps=2)
+    run_parity(name, range(16, 32), p_invalid=0.3)
+
+
+@pytest.mark.parametrize("name", ["B", "S_rect", "S_rect_full"])
+def test_rect(name):
+    run_parity(name, range(64), extra_steps=2)
+    run_parity(name, range(64, 96), p_invalid=0.2)
+
+
+@pytest.mark.parametrize("name", ["C", "S_pin_tight", "REF_pin"])
+def test_pin_centroid(name):
+    st = {}
+    run_parity(name, range(64), extra_steps=2, stats=st)
+    run_parity(name, range(64, 96), p_invalid=0.1, stats=st)
+    assert st["reward_inexact"] == 0, st  # float64 rewards bit-identical
+
+
+@pytest.mark.parametrize("name", ["C_both", "C_beam", "S_pin", "S_pin_beam3"])
+def test_pin_beam(name):
+    st = {}
+    run_parity(name, range(64), extra_steps=2, stats=st)
+    run_parity(name, range(64, 96), p_invalid=0.1, stats=st)
+    assert st["reward_inexact"] == 0, st
+
+
+@pytest.mark.parametrize("name", ["D", "D_both", "S_spa", "S_spa_tight"])
+def test_spatial(name):
+    st = {}
+    run_parity(name, range(48), extra_steps=2, stats=st)
+    run_parity(name, range(48, 64), p_invalid=0.1, stats=st)
+    assert st["reward_inexact"] == 0, st
+
+
+def test_large_grid_E():
+    run_parity("E", range(8))
+
+
+@pytest.mark.parametrize("name", ["A", "B", "C", "D", "S_pin_tight"])
+def test_autoreset(name):
+    run_parity(name, range(32), autoreset=True, episodes=3)
+    run_parity(name, range(32, 48), autoreset=True, episodes=3, p_invalid=0.1)
