@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched placement environments on B200.
+
+Metric (BASELINE.json): env-steps/sec, whole job, device-timed, on the random-
+policy rollout { device random policy -> step -> terminal reward -> auto-reset }
+of config C (dummy_env_rectangular_pin 32x32, 10 components, 5 nets, centroid
+reward, 65 536 envs per GPU); weak scaling over GPUs, no collective on the step
+path.  One JSON line on rank 0:
+  value        device-timed, actions sampled on device, everything resident in HBM
+  e2e          same rollout through pcb_step_host: actions from pinned host memory
+               (H2D every step), reward + done read back (D2H every step)
+  roofline     the step kernel: algorithmic bytes per launch / its CUDA-event time
+  cpu_baseline the oracle port (numpy restatement of the reference) on the host
+               cores as a multiprocess vector env, bounded sample
+`--impl reference` times that CPU path alone with all host cores.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOAD = "C"
+ENVS_PER_GPU = 65536
+OBS_RING = 4
+# SURVEY.md section 8d / BASELINE.md section 5: algorithmic bytes per env-step (compact contract)
+ALGO_BYTES = {"A": 161, "B": 1049, "C": 7699, "D": 15775, "E": 28821}
+EP_LEN = {"A": 4, "B": 6, "C": 10, "D": 10, "E": 32}
+WORKLOAD_DESC = {
+    "B": "B: dummy_env_rectangular 16x16, 6 rectangular components",
+    "C": "C: dummy_env_rectangular_pin 32x32, 10 components, 5 nets, <=6 pins/net, centroid reward",
+    "D": "D: dummy_env_rectangular_pin_spatial 32x32, 10 components, 5 nets, centroid reward",
+    "E": "E: dummy_env_rectangular_pin 64x64, 32 components, 16 nets, centroid reward",
+}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------
+# CPU baseline: the oracle port as a multiprocess vector env
+# ----------------------------------------------------------------------------
+def _cpu_worker(args):
+    name, wid, budget = args
+    import random
+
+    import numpy as np
+
+    from ref_harness import CONFIGS, make_oracle
+
+    np.random.seed(wid)
+    random.seed(wid)
+    rng = np.random.default_rng(wid)
+    env = make_oracle(CONFIGS[name])
+    steps = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < budget:
+        env.reset()
+        done = False
+        while not done:
+            valid = np.flatnonzero(env.action_mask)
+            a = np.unravel_index(valid[rng.integers(0, len(valid))], env.action_mask.shape)
+            _, _, done, _ = env.step(tuple(int(v) for v in a))
+            steps += 1
+    return steps, time.perf_counter() - t0
+
+
+def cpu_baseline(name, budget_s, procs=None):
+    procs = procs or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_cpu_worker, [(name, w, budget_s) for w in range(procs)])
+    wall = time.perf_counter() - t0
+    rate = sum(s / t for s, t in res)
+    return {"value": rate, "unit": "env-steps/s", "cores": procs, "kind": "port",
+            "sample": f"config {name}, random valid policy, {procs} processes x {budget_s:.0f} s "
+                      f"({sum(s for s, _ in res)} env-steps, wall {wall:.1f} s); oracle/ numpy port "
+                      "of the reference envs (reference itself is Python and absent on the GPU box)"}
+
+
+# ----------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for row in self.rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------
+def stagger(env, name, seed):
+    """De-synchronise the episodes: after this, env i is (EP_LEN-1 - i % EP_LEN) steps
+    into its episode, so every step finishes ~1/EP_LEN of the envs (steady state of a
+    real rollout) instead of all of them every EP_LEN-th step."""
+    import torch
+
+    L = EP_LEN[name]
+    ids = torch.arange(env.num_envs, device=env.device)
+    for j in range(L):
+        env.rollout_random(1, seed)
+        env.reset(mask=((ids % L) == j))
+
+
+def gpu_arm(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+
+    ge.build()
+    import pcbgpu
+    from ref_harness import CONFIGS
+
+    name = args.workload
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    N = args.envs
+    cfg = CONFIGS[name]
+    env = pcbgpu.PcbVecEnv(cfg, N, device=local_rank, autoreset=True, obs_ring=OBS_RING,
+                           bank_size=N * 4, seed=1000 + rank)
+    seed = 7 + rank
+    K, W = args.steps, args.warmup
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def prepare():
+        env.reset()
+        stagger(env, name, seed)
+        env.rollout_random(W, seed)
+        env.episode_stats(reset=True)
+
+    # ---- pass 1: device-timed, device policy (value) -------------------------
+    prepare()
+    width = env.spec.action_width
+    log = torch.zeros((K, N, width), dtype=torch.int32, device=env.device)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    l0 = env.launch_count
+    t_wall0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    env.rollout_random(K, seed)
+    e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    launches = env.launch_count - l0
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    stats = env.episode_stats(reset=True)
+
+    # ---- pass 2: same rollout with per-kernel CUDA events (roofline) + action log ----
+    prepare()
+    env.kernel_timing(True)
+    barrier()
+    env.rollout_random(K, seed, actions_log=log)
+    barrier()
+    kt = env.kernel_times()
+    env.kernel_timing(False)
+    stats2 = env.episode_stats(reset=True)
+
+    # ---- pass 3: end to end through host buffers (e2e) ---------------------------
+    import numpy as np
+
+    h_actions = torch.empty((K, N, width), dtype=torch.int32, pin_memory=True)
+    h_actions.copy_(log)
+    del log
+    h_reward = torch.empty((N,), dtype=torch.float64, pin_memory=True)
+    h_done = torch.empty((N,), dtype=torch.uint8, pin_memory=True)
+    a_np, r_np, d_np = h_actions.numpy(), h_reward.numpy(), h_done.numpy()
+    prepare()
+    barrier()
+    t0 = time.perf_counter()
+    checksum = 0.0
+    for t in range(K):
+        env.step_host(a_np[t], r_np, d_np)
+        checksum += float(d_np[0])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    stats3 = env.episode_stats(reset=True)
+
+    # ---- reduce over ranks ------------------------------------------------------
+    vals = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=env.device)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        agg = pcbgpu.allreduce_episode_stats  # noqa: F841 (C1: the only collective, off the step path)
+    ms_max, e2e_ms_max = vals.tolist()
+    total_steps = float(N) * K * world
+    value = total_steps / (ms_max * 1e-3)
+    e2e_value = total_steps / (e2e_ms_max * 1e-3)
+
+    if rank != 0:
+        return
+    peak, peak_src = load_peaks()
+    step_ms, step_n = kt["step"]
+    term_ms, term_n = kt["terminal"]
+    samp_ms, samp_n = kt["sample"]
+    done_frac = stats2["episodes"] / (float(N) * K)
+    # with the fused terminal path (centroid reward) the step kernel also writes the first
+    # observation of every restarting env; otherwise terminal_kernel writes those
+    fused = term_n == 0
+    written = float(N) if fused else N * (1.0 - done_frac)
+    bytes_per_launch = ALGO_BYTES[name] * written
+    avg_step_s = step_ms * 1e-3 / max(step_n, 1)
+    achieved = bytes_per_launch / avg_step_s / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(f"{name}:step_kernel")
+    out = {
+        "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {
+            "workload": WORKLOAD_DESC[name], "envs_per_gpu": N, "policy": "uniform random over valid "
+            "actions, sampled on device (Philox)", "autoreset": True,
+            "instances": f"{N * 4} per GPU from the library generator (distribution of the reference's generate_instances)",
+            "episode_phases": "staggered (1/%d of the envs finish every step)" % EP_LEN[name],
+            "l2": "working set larger than L2: every step writes a fresh %.0f MB observation slice "
+                  "(ring of %d slices)" % (N * (ALGO_BYTES[name]) / 1e6, OBS_RING),
+            "timing": "CUDA events on the launching stream around %d steps, max over ranks" % K,
+        },
+        "e2e": {"value": e2e_value, "unit": "env-steps/s",
+                "h2d_bytes_per_step": int(N * width * 4), "d2h_bytes_per_step": int(N * 9),
+                "path": "pcb_step_host (C ABI): pinned host actions -> H2D -> step -> D2H reward+done, "
+                        "sync every step; observations stay on device (DLPack)"},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "kernel": "step_kernel",
+                     "peak_source": peak_src,
+                     "algorithmic_bytes_per_env_step": ALGO_BYTES[name],
+                     "envs_written_per_launch": written,
+                     "avg_launch_us": avg_step_s * 1e6,
+                     "whole_step_frac": value / world * ALGO_BYTES[name] / 1e9 / peak,
+                     "kernel_share_ms": {"step": step_ms, "terminal": term_ms, "sample": samp_ms}},
+        "episodes": {"device_pass": stats["episodes"], "timed_kernel_pass": stats2["episodes"],
+                     "e2e_pass": stats3["episodes"],
+                     "mean_return": stats["sum_return"] / max(stats["episodes"], 1),
+                     "mean_length": stats["sum_length"] / max(stats["episodes"], 1)},
+        "wall_s_timed_region": wall,
+    }
+    if world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(name, args.cpu_seconds)
+    else:
+        out["cpu_baseline"] = None
+    print(json.dumps(out), flush=True)
+
+
+def reference_arm(args, rank, world):
+    """The reference's CPU implementation of the path on the host cores.  The reference
+    is pure Python and is not present on the GPU box, so this times the oracle port
+    (oracle/: same numpy/scipy operations per step) with one process per core."""
+    if rank != 0:
+        return
+    name = args.workload
+    procs = os.cpu_count() or 1
+    K, W = args.steps, args.warmup
+    # a "step" = a bounded sample; the whole run is sized to stay within a few minutes
+    per_step = max(0.5, min(4.0, 120.0 / max(K + W, 1)))
+    for _ in range(min(W, 1)):
+        cpu_baseline(name, 0.5, procs)
+    t0 = time.perf_counter()
+    rates = []
+    reps = max(1, min(K, int(120.0 / per_step)))
+    for _ in range(reps):
+        rates.append(cpu_baseline(name, per_step, procs)["value"])
+    wall = time.perf_counter() - t0
+    value = sum(rates) / len(rates)
+    out = {
+        "impl": "reference", "metric": "env-steps/sec", "value": value, "unit": "env-steps/s",
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": per_step * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD_DESC[name], "policy": "uniform random over valid actions",
+                   "note": "CPU multiprocess vector env, %d samples of %.1f s" % (reps, per_step)},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": procs, "kind": "port",
+                         "sample": f"{reps} x {per_step:.1f} s x {procs} processes, config {name}, wall {wall:.0f} s"},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=256)
+    ap.add_argument("--warmup", type=int, default=32)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=WORKLOAD, choices=sorted(WORKLOAD_DESC))
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+    gpu_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -172,6 +172,18 @@ int pcb_get_occupancy(pcb_env_t* env, uint64_t* h_rows, void* stream);
 /* Number of kernels this handle has launched so far (bench: gpu_launches). */
 int64_t pcb_launch_count(pcb_env_t* env);
 
+/* simulate() of agent/random/random_policy_*.py:25-58 for all envs: n_steps times
+ * { pcb_sample_random_actions; pcb_step } issued from one call.  d_actions_log is
+ * NULL or a device buffer [n_steps, N, 2|3] int32 that receives every action. */
+int pcb_rollout_random(pcb_env_t* env, uint64_t seed, int n_steps, int32_t* d_actions_log,
+                       void* stream);
+
+/* Measurement aid: when on, every kernel launch is bracketed by CUDA events on the
+ * launching stream.  pcb_kernel_times waits for them and returns the summed device
+ * time [ms] and launch count per kernel {step, terminal, reset, sample}, then clears. */
+int pcb_enable_kernel_timing(pcb_env_t* env, int on);
+int pcb_kernel_times(pcb_env_t* env, double ms[4], int64_t launches[4]);
+
 const char* pcb_last_error(void);
 int pcb_abi_version(void);
 

@@ -11,7 +11,8 @@ SYMBOLS = (
     "pcb_create", "pcb_destroy", "pcb_upload_instances", "pcb_generate_instances", "pcb_reset",
     "pcb_step", "pcb_sample_random_actions", "pcb_step_host", "pcb_get_tensor",
     "pcb_current_slice", "pcb_episode_stats", "pcb_get_occupancy", "pcb_launch_count",
-    "pcb_last_error", "pcb_abi_version",
+    "pcb_last_error", "pcb_abi_version", "pcb_rollout_random", "pcb_enable_kernel_timing",
+    "pcb_kernel_times",
 )
 
 
@@ -73,6 +74,9 @@ def load():
     lib.pcb_get_occupancy.argtypes = [vp, vp, vp]
     lib.pcb_launch_count.argtypes = [vp]
     lib.pcb_launch_count.restype = i64
+    lib.pcb_rollout_random.argtypes = [vp, u64, i32, vp, vp]
+    lib.pcb_enable_kernel_timing.argtypes = [vp, i32]
+    lib.pcb_kernel_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
     lib.pcb_last_error.restype = ctypes.c_char_p
     lib.pcb_abi_version.restype = i32
     if lib.pcb_abi_version() != ABI_VERSION:

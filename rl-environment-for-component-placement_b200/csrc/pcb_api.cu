@@ -69,9 +69,17 @@ struct pcb_env {
   uint32_t bank_count;
   Out base;  // slice 0 pointers
   double* stats;
-  int32_t* d_actions;  // staging for pcb_step_host
+  int32_t* d_actions;  // staging for pcb_step_host / ping-pong of pcb_rollout_random
+  int32_t* d_actions2;
+  float* ratio_lut;
+  int shape_id;        // 0 = generic (DynShape), 1..4 = ShapeB/C/D/E
+  bool fuse;           // step_kernel finishes episodes itself
   std::vector<TensorDesc> tensors;
   std::vector<void*> allocs;
+  // optional per-kernel CUDA-event timing (pcb_enable_kernel_timing)
+  bool timing;
+  struct Timed { int id; cudaEvent_t a, b; };
+  std::vector<Timed> timed;
 };
 
 namespace {
@@ -86,15 +94,15 @@ Out slice_ptrs(const pcb_env* e, int slice) {
   const Dims& d = e->d;
   const size_t N = (size_t)e->n_envs, s = (size_t)slice;
   Out o = e->base;
-  if (o.grid) o.grid += s * N * d.grid_b;
-  if (o.mask) o.mask += s * N * d.mask_b;
-  if (o.feat) o.feat += s * N * d.feat_n;
+  if (o.grid) o.grid += s * N * d.L.grid_b;
+  if (o.mask) o.mask += s * N * d.L.mask_b;
+  if (o.feat) o.feat += s * N * d.L.feat_n;
   if (o.comp_mask) o.comp_mask += s * N * d.C;
   if (o.place_mask) o.place_mask += s * N * d.C;
-  if (o.pnum) o.pnum += s * N * d.pnum_n;
-  if (o.pcat) o.pcat += s * N * d.pcat_n;
-  if (o.pgrid) o.pgrid += s * N * d.pgrid_b;
-  if (o.cgrid) o.cgrid += s * N * d.cgrid_b;
+  if (o.pnum) o.pnum += s * N * d.L.pnum_n;
+  if (o.pcat) o.pcat += s * N * d.L.pcat_n;
+  if (o.pgrid) o.pgrid += s * N * d.L.pgrid_b;
+  if (o.cgrid) o.cgrid += s * N * d.L.cgrid_b;
   return o;
 }
 
@@ -109,30 +117,81 @@ Params make_params(const pcb_env* e) {
   p.n_envs = e->n_envs;
   p.stats = e->stats;
   p.step_no = e->step_no;
+  p.ratio_lut = e->ratio_lut;
+  p.fuse_terminal = e->fuse ? 1 : 0;
   return p;
 }
 
 enum KernelId { K_STEP, K_TERM, K_RESET, K_SAMPLE };
 
+template <typename S>
+bool shape_matches(const Dims& d) {
+  S sh(d);
+  return d.kind == sh.kind() && d.H == sh.H() && d.W == sh.W() && d.C == sh.C() && d.mh == sh.mh() &&
+         d.mw == sh.mw() && d.K == sh.K() && d.max_pins == sh.max_pins();
+}
+
+int pick_shape(const Dims& d) {
+  // host-side mirror of the FixedShape parameters (pcb_kernels.cuh)
+  auto is = [&](int kind, int H, int W, int C, int mh, int mw, int K, int mp) {
+    return d.kind == kind && d.H == H && d.W == W && d.C == C && d.mh == mh && d.mw == mw &&
+           d.K == K && d.max_pins == mp;
+  };
+  if (is(1, 16, 16, 6, 4, 4, 0, 0)) return 1;
+  if (is(2, 32, 32, 10, 4, 4, 6, 30)) return 2;
+  if (is(3, 32, 32, 10, 4, 4, 6, 30)) return 3;
+  if (is(2, 64, 64, 32, 4, 4, 17, 96)) return 4;
+  return 0;
+}
+
+template <int RPL, typename T, typename S>
+int launch_shape(KernelId id, dim3 grid, dim3 block, size_t sm, cudaStream_t st, const Params& p) {
+  switch (id) {
+    case K_STEP: step_kernel<RPL, T, S><<<grid, block, sm, st>>>(p); break;
+    case K_RESET: reset_kernel<RPL, T, S><<<grid, block, sm, st>>>(p); break;
+    default: break;
+  }
+  return 0;
+}
+
+template <int RPL, typename T, typename S>
+int set_smem_shape(size_t bytes) {
+  int rc = set_smem(step_kernel<RPL, T, S>, bytes);
+  if (rc) return rc;
+  return set_smem(reset_kernel<RPL, T, S>, bytes);
+}
+
 int launch(pcb_env* e, KernelId id, const Params& p, cudaStream_t st) {
   dim3 grid((e->n_envs + kWarpsPerCta - 1) / kWarpsPerCta), block(kWarpsPerCta * 32);
   size_t sm = id == K_SAMPLE ? 0 : e->smem_bytes;
-  if (e->wide) {
-    switch (id) {
-      case K_STEP: step_kernel<2, uint64_t><<<grid, block, sm, st>>>(p); break;
-      case K_TERM: terminal_kernel<2, uint64_t><<<grid, block, sm, st>>>(p); break;
-      case K_RESET: reset_kernel<2, uint64_t><<<grid, block, sm, st>>>(p); break;
-      case K_SAMPLE: sample_kernel<2, uint64_t><<<grid, block, sm, st>>>(p); break;
-    }
+  pcb_env::Timed tm{(int)id, nullptr, nullptr};
+  if (e->timing) {
+    CU(cudaEventCreate(&tm.a));
+    CU(cudaEventCreate(&tm.b));
+    CU(cudaEventRecord(tm.a, st));
+  }
+  if (id == K_TERM) {
+    if (e->wide) terminal_kernel<2, uint64_t><<<grid, block, sm, st>>>(p);
+    else terminal_kernel<1, uint32_t><<<grid, block, sm, st>>>(p);
+  } else if (id == K_SAMPLE) {
+    if (e->wide) sample_kernel<2, uint64_t><<<grid, block, sm, st>>>(p);
+    else sample_kernel<1, uint32_t><<<grid, block, sm, st>>>(p);
   } else {
-    switch (id) {
-      case K_STEP: step_kernel<1, uint32_t><<<grid, block, sm, st>>>(p); break;
-      case K_TERM: terminal_kernel<1, uint32_t><<<grid, block, sm, st>>>(p); break;
-      case K_RESET: reset_kernel<1, uint32_t><<<grid, block, sm, st>>>(p); break;
-      case K_SAMPLE: sample_kernel<1, uint32_t><<<grid, block, sm, st>>>(p); break;
+    switch (e->shape_id) {
+      case 1: launch_shape<1, uint32_t, ShapeB>(id, grid, block, sm, st, p); break;
+      case 2: launch_shape<1, uint32_t, ShapeC>(id, grid, block, sm, st, p); break;
+      case 3: launch_shape<1, uint32_t, ShapeD>(id, grid, block, sm, st, p); break;
+      case 4: launch_shape<2, uint64_t, ShapeE>(id, grid, block, sm, st, p); break;
+      default:
+        if (e->wide) launch_shape<2, uint64_t, DynShape>(id, grid, block, sm, st, p);
+        else launch_shape<1, uint32_t, DynShape>(id, grid, block, sm, st, p);
     }
   }
   CU(cudaGetLastError());
+  if (e->timing) {
+    CU(cudaEventRecord(tm.b, st));
+    e->timed.push_back(tm);
+  }
   e->launches += 1;
   return 0;
 }
@@ -189,43 +248,15 @@ int check_config(const pcb_config_t* c) {
   return 0;
 }
 
-void fill_dims(const pcb_config_t& c, bool wide, Dims& d) {
+void fill_dims(const pcb_config_t& c, Dims& d) {
   memset(&d, 0, sizeof d);
   d.kind = c.kind; d.H = c.height; d.W = c.width;
-  d.O = c.kind == 0 ? 1 : (c.kind == 1 ? 2 : 4);
   d.sq_n = c.component_n;
-  if (c.kind != 0) {
-    d.C = c.max_num_components; d.mh = c.max_component_h; d.mw = c.max_component_w;
-    d.P = d.mh * d.mw;
-    d.F = c.kind == 3 ? 5 + d.P : 5;
-  }
+  if (c.kind != 0) { d.C = c.max_num_components; d.mh = c.max_component_h; d.mw = c.max_component_w; }
   if (c.kind >= 2) { d.K = c.max_num_nets + 1; d.max_pins = c.max_pins; }
   d.reward_type = c.reward_type; d.beam_width = c.reward_beam_width;
   d.norm_fma = c.norm_uses_fma; d.autoreset = c.autoreset;
-  const int word = wide ? 8 : 4, rows = wide ? 64 : 32;
-  d.st_comps = 32;
-  d.st_pins = d.st_comps + align16(d.C * 4);
-  d.st_occ = d.st_pins + align16(d.max_pins * 8);
-  d.st_stride = align16(d.st_occ + rows * word);
-  d.rec_comps = 16;
-  d.rec_pins = d.rec_comps + align16(d.C * 4);
-  d.rec_stride = d.rec_pins + align16(d.max_pins * 8);
-  d.grid_b = d.H * d.W;
-  d.mask_b = d.O * d.H * d.W;
-  d.feat_n = d.C * d.F;
-  if (c.kind == 2) { d.pnum_n = d.C * d.P * 4; d.pcat_n = d.C * d.P; }
-  if (c.kind == 3) {
-    d.pnum_n = (d.C * d.P + 1) * 4; d.pcat_n = (d.C * d.P + 1) * 2;
-    d.pgrid_b = d.H * d.W * d.K; d.cgrid_b = d.C * d.mh * d.mw * d.K;
-  }
-  int stage = 16;
-  stage = std::max(stage, (d.pnum_n + d.pcat_n) * 2);
-  if (c.kind == 3) stage = std::max({stage, d.feat_n * 4, d.pgrid_b, d.cgrid_b});
-  d.sm_mrow = d.st_stride;
-  d.sm_stage = d.sm_mrow + 2 * rows * word;
-  d.sm_scr = d.sm_stage + align16(stage) + 16;
-  int scr = c.kind >= 2 ? route_scratch_bytes(d.max_pins, d.K) : 0;
-  d.sm_stride = align16(d.sm_scr + scr);
+  d.L = make_layout(d.kind, d.H, d.W, d.C, d.mh, d.mw, d.K, d.max_pins);
   d.ww = c.weight_wirelength; d.wi = c.weight_num_intersections;
   d.wl_norm = c.wirelength_norm; d.ni_norm = c.intersections_norm;
   d.pen_reward = c.penalty_reward; d.pen_wl = c.penalty_wirelength; d.pen_ni = c.penalty_intersections;
@@ -247,15 +278,15 @@ int pack_and_upload(pcb_env* e, const pcb_instance_bank_t* b) {
     return fail(PCB_ERR_INVALID, "pin arrays missing in the instance bank");
   if (b->count > 0x7fffffffLL) return fail(PCB_ERR_INVALID, "too many instances");
   const size_t cnt = (size_t)b->count;
-  std::vector<uint8_t> host(cnt * d.rec_stride, 0);
+  std::vector<uint8_t> host(cnt * d.L.rec_stride, 0);
   std::vector<int> last(kMaxComps * 256);
   for (size_t i = 0; i < cnt; ++i) {
-    uint8_t* rec = host.data() + i * d.rec_stride;
+    uint8_t* rec = host.data() + i * d.L.rec_stride;
     EnvHdr* h = reinterpret_cast<EnvHdr*>(rec);
     int nc = b->n_comp[i];
     if (nc < 1 || nc > d.C) return fail(PCB_ERR_INVALID, "instance %zu: n_comp %d outside 1..%d", i, nc, d.C);
     h->n_comp = (uint8_t)nc;
-    CompRec* comps = reinterpret_cast<CompRec*>(rec + d.rec_comps);
+    CompRec* comps = reinterpret_cast<CompRec*>(rec + d.L.rec_comps);
     for (int c = 0; c < nc; ++c) {
       int ch = b->comp_h[i * d.C + c], cw = b->comp_w[i * d.C + c];
       if (ch < 1 || cw < 1 || ch > d.mh || cw > d.mw)
@@ -268,7 +299,7 @@ int pack_and_upload(pcb_env* e, const pcb_instance_bank_t* b) {
     if (nn < 0 || nn >= d.K) return fail(PCB_ERR_INVALID, "instance %zu: n_nets %d outside 0..%d", i, nn, d.K - 1);
     h->n_pins = (uint16_t)np;
     h->n_nets = (uint8_t)nn;
-    PinRec* pins = reinterpret_cast<PinRec*>(rec + d.rec_pins);
+    PinRec* pins = reinterpret_cast<PinRec*>(rec + d.L.rec_pins);
     std::fill(last.begin(), last.begin() + (size_t)nc * 256, -1);
     int rank[kMaxComps] = {0};
     int prev_net = 0;
@@ -283,7 +314,7 @@ int pack_and_upload(pcb_env* e, const pcb_instance_bank_t* b) {
       if (r.net >= nn || r.net < prev_net)
         return fail(PCB_ERR_INVALID, "instance %zu pin %d: pins must be net-major, net %d", i, q, r.net);
       prev_net = r.net;
-      int max_row = d.kind == 3 ? d.C * d.P : d.P;
+      int max_row = d.kind == 3 ? d.C * d.L.P : d.L.P;
       if (r.pin_id >= max_row) return fail(PCB_ERR_INVALID, "instance %zu pin %d: pin_id %d >= %d", i, q, r.pin_id, max_row);
       r.rank = (uint8_t)rank[r.comp]++;
       // last writer of a (component, pin_id) feature row wins (update_all_pins_feature,
@@ -299,6 +330,15 @@ int pack_and_upload(pcb_env* e, const pcb_instance_bank_t* b) {
     if (d.kind == 2)
       for (int q = 0; q < np; ++q)
         if (last[pins[q].comp * 256 + pins[q].pin_id] == q) pins[q].flags = kPinWinner;
+    if (d.reward_type != PCB_REWARD_CENTROID) {  // the beam router keeps a net in registers
+      int run = 0;
+      for (int q = 0; q < np; ++q) {
+        run = (q > 0 && pins[q].net == pins[q - 1].net) ? run + 1 : 1;
+        if (run > kMaxBeamPoints + 1)
+          return fail(PCB_ERR_INVALID, "instance %zu: net %d has more than %d pins (beam route limit)",
+                      i, pins[q].net, kMaxBeamPoints + 1);
+      }
+    }
   }
   if (e->bank) { cudaFree(e->bank); e->bank = nullptr; }
   void* p = nullptr;
@@ -330,42 +370,57 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
   e->cfg = *cfg;
   e->device = device; e->n_envs = num_envs; e->ring = cfg->obs_ring; e->slice = 0;
   e->wide = cfg->height > 32 || cfg->width > 32;
-  e->step_no = 0; e->launches = 0; e->bank = nullptr; e->bank_count = 0;
+  e->step_no = 0; e->launches = 0; e->bank = nullptr; e->bank_count = 0; e->timing = false;
+  e->ratio_lut = nullptr; e->d_actions = nullptr; e->d_actions2 = nullptr;
   memset(&e->base, 0, sizeof e->base);
-  fill_dims(*cfg, e->wide, e->d);
+  fill_dims(*cfg, e->d);
   const Dims& d = e->d;
-  e->smem_bytes = (size_t)d.sm_stride * kWarpsPerCta;
+  e->smem_bytes = (size_t)d.L.sm_stride * kWarpsPerCta;
   if (e->smem_bytes > 200 * 1024) {
     delete e;
     return fail(PCB_ERR_INVALID, "configuration needs %zu bytes of shared memory per CTA", e->smem_bytes);
   }
   auto cleanup = [&](int code) { pcb_destroy(e); return code; };
 #define TRY(x) do { int rc_ = (x); if (rc_) return cleanup(rc_); } while (0)
-  if (e->wide) {
-    TRY(set_smem(step_kernel<2, uint64_t>, e->smem_bytes));
-    TRY(set_smem(terminal_kernel<2, uint64_t>, e->smem_bytes));
-    TRY(set_smem(reset_kernel<2, uint64_t>, e->smem_bytes));
-  } else {
-    TRY(set_smem(step_kernel<1, uint32_t>, e->smem_bytes));
-    TRY(set_smem(terminal_kernel<1, uint32_t>, e->smem_bytes));
-    TRY(set_smem(reset_kernel<1, uint32_t>, e->smem_bytes));
+  e->shape_id = cfg->reserved0 == 1 ? 0 : pick_shape(e->d);  // reserved0 == 1 forces the generic kernels (tests)
+  e->fuse = d.kind < 2 || d.reward_type == PCB_REWARD_CENTROID;
+  switch (e->shape_id) {
+    case 1: TRY((set_smem_shape<1, uint32_t, ShapeB>(e->smem_bytes))); break;
+    case 2: TRY((set_smem_shape<1, uint32_t, ShapeC>(e->smem_bytes))); break;
+    case 3: TRY((set_smem_shape<1, uint32_t, ShapeD>(e->smem_bytes))); break;
+    case 4: TRY((set_smem_shape<2, uint64_t, ShapeE>(e->smem_bytes))); break;
+    default:
+      if (e->wide) TRY((set_smem_shape<2, uint64_t, DynShape>(e->smem_bytes)));
+      else TRY((set_smem_shape<1, uint32_t, DynShape>(e->smem_bytes)));
   }
+  if (e->wide) TRY(set_smem(terminal_kernel<2, uint64_t>, e->smem_bytes));
+  else TRY(set_smem(terminal_kernel<1, uint32_t>, e->smem_bytes));
   const size_t N = (size_t)num_envs, R = (size_t)e->ring;
   const int64_t n64 = num_envs, r64 = e->ring;
-  TRY(dev_alloc(e, &e->state, N * d.st_stride));
+  TRY(dev_alloc(e, &e->state, N * d.L.st_stride));
   TRY(dev_alloc(e, &e->stats, kStatSlots * 8 * sizeof(double)));
   TRY(dev_alloc(e, &e->d_actions, N * 3 * sizeof(int32_t)));
+  TRY(dev_alloc(e, &e->d_actions2, N * 3 * sizeof(int32_t)));
+  {
+    // area ratio h*w/(H*W): float64 quotient rounded to float32, i.e. np.float32(reference value)
+    const int nlut = d.mh * d.mw + 1;
+    std::vector<float> lut(nlut > 0 ? nlut : 1, 0.f);
+    for (int a = 0; a < nlut; ++a) lut[a] = (float)((double)a / (double)(d.H * d.W));
+    TRY(dev_alloc(e, &e->ratio_lut, lut.size() * sizeof(float)));
+    cudaError_t ce = cudaMemcpy(e->ratio_lut, lut.data(), lut.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) return cleanup(fail(PCB_ERR_CUDA, "cudaMemcpy(ratio_lut): %s", cudaGetErrorString(ce)));
+  }
   auto add = [&](const char* key, void** ptr, int code, int bits, std::vector<int64_t> shape, bool ringed) {
     e->tensors.push_back(TensorDesc{key, ptr, code, bits, std::move(shape), ringed});
   };
-  TRY(dev_alloc(e, &e->base.grid, R * N * d.grid_b));
+  TRY(dev_alloc(e, &e->base.grid, R * N * d.L.grid_b));
   add("grid", (void**)&e->base.grid, kDLUInt, 8, {r64, n64, d.H, d.W}, true);
-  TRY(dev_alloc(e, &e->base.mask, R * N * d.mask_b));
+  TRY(dev_alloc(e, &e->base.mask, R * N * d.L.mask_b));
   if (d.kind == 0) add("action_mask", (void**)&e->base.mask, kDLUInt, 8, {r64, n64, d.H, d.W}, true);
-  else add("action_mask", (void**)&e->base.mask, kDLUInt, 8, {r64, n64, d.O, d.H, d.W}, true);
+  else add("action_mask", (void**)&e->base.mask, kDLUInt, 8, {r64, n64, d.L.O, d.H, d.W}, true);
   if (d.kind >= 1) {
-    TRY(dev_alloc(e, &e->base.feat, R * N * d.feat_n * sizeof(float)));
-    add("all_components_feature", (void**)&e->base.feat, kDLFloat, 32, {r64, n64, d.C, d.F}, true);
+    TRY(dev_alloc(e, &e->base.feat, R * N * d.L.feat_n * sizeof(float)));
+    add("all_components_feature", (void**)&e->base.feat, kDLFloat, 32, {r64, n64, d.C, d.L.F}, true);
     TRY(dev_alloc(e, &e->base.place_mask, R * N * d.C));
     add("placement_mask", (void**)&e->base.place_mask, kDLUInt, 8, {r64, n64, d.C}, true);
   }
@@ -374,17 +429,17 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
     add("component_mask", (void**)&e->base.comp_mask, kDLUInt, 8, {r64, n64, d.C}, true);
   }
   if (d.kind >= 2) {
-    TRY(dev_alloc(e, &e->base.pnum, R * N * d.pnum_n * sizeof(int16_t)));
-    TRY(dev_alloc(e, &e->base.pcat, R * N * d.pcat_n * sizeof(int16_t)));
+    TRY(dev_alloc(e, &e->base.pnum, R * N * d.L.pnum_n * sizeof(int16_t)));
+    TRY(dev_alloc(e, &e->base.pcat, R * N * d.L.pcat_n * sizeof(int16_t)));
     if (d.kind == 2) {
-      add("all_pins_num_feature", (void**)&e->base.pnum, kDLInt, 16, {r64, n64, d.C, d.P, 4}, true);
-      add("all_pins_cat_feature", (void**)&e->base.pcat, kDLInt, 16, {r64, n64, d.C, d.P, 1}, true);
+      add("all_pins_num_feature", (void**)&e->base.pnum, kDLInt, 16, {r64, n64, d.C, d.L.P, 4}, true);
+      add("all_pins_cat_feature", (void**)&e->base.pcat, kDLInt, 16, {r64, n64, d.C, d.L.P, 1}, true);
     } else {
-      add("all_pins_num_feature", (void**)&e->base.pnum, kDLInt, 16, {r64, n64, d.C * d.P + 1, 4}, true);
-      add("all_pins_cat_feature", (void**)&e->base.pcat, kDLInt, 16, {r64, n64, d.C * d.P + 1, 2}, true);
-      TRY(dev_alloc(e, &e->base.pgrid, R * N * d.pgrid_b));
+      add("all_pins_num_feature", (void**)&e->base.pnum, kDLInt, 16, {r64, n64, d.C * d.L.P + 1, 4}, true);
+      add("all_pins_cat_feature", (void**)&e->base.pcat, kDLInt, 16, {r64, n64, d.C * d.L.P + 1, 2}, true);
+      TRY(dev_alloc(e, &e->base.pgrid, R * N * d.L.pgrid_b));
       add("pin_grid", (void**)&e->base.pgrid, kDLUInt, 8, {r64, n64, d.H, d.W, d.K}, true);
-      TRY(dev_alloc(e, &e->base.cgrid, R * N * d.cgrid_b));
+      TRY(dev_alloc(e, &e->base.cgrid, R * N * d.L.cgrid_b));
       add("component_grid", (void**)&e->base.cgrid, kDLUInt, 8, {r64, n64, d.C, d.mh, d.mw, d.K}, true);
     }
   }
@@ -463,7 +518,8 @@ int pcb_reset(pcb_env_t* e, const uint8_t* d_reset_mask, void* stream) {
   return launch(e, K_RESET, p, st);
 }
 
-int pcb_step(pcb_env_t* e, const int32_t* d_actions, int action_format, void* stream) {
+static int step_impl(pcb_env_t* e, const int32_t* d_actions, int action_format, uint64_t seed,
+                     int32_t* d_next_actions, void* stream) {
   int rc = ready(e);
   if (rc) return rc;
   if (!d_actions) return fail(PCB_ERR_INVALID, "d_actions is NULL");
@@ -475,11 +531,17 @@ int pcb_step(pcb_env_t* e, const int32_t* d_actions, int action_format, void* st
   Params p = make_params(e);
   p.actions = d_actions;
   p.action_format = action_format;
+  p.seed = seed;
+  p.actions_out = d_next_actions;
   rc = launch(e, K_STEP, p, st);
   if (rc) return rc;
-  rc = launch(e, K_TERM, p, st);
+  if (!e->fuse) rc = launch(e, K_TERM, p, st);
   e->step_no += 1;
   return rc;
+}
+
+int pcb_step(pcb_env_t* e, const int32_t* d_actions, int action_format, void* stream) {
+  return step_impl(e, d_actions, action_format, 0, nullptr, stream);
 }
 
 int pcb_sample_random_actions(pcb_env_t* e, uint64_t seed, int32_t* d_actions, void* stream) {
@@ -555,11 +617,11 @@ int pcb_get_occupancy(pcb_env_t* e, uint64_t* h_rows, void* stream) {
   CU(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream;
   const Dims& d = e->d;
-  std::vector<uint8_t> host((size_t)e->n_envs * d.st_stride);
+  std::vector<uint8_t> host((size_t)e->n_envs * d.L.st_stride);
   CU(cudaMemcpyAsync(host.data(), e->state, host.size(), cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   for (int i = 0; i < e->n_envs; ++i) {
-    const uint8_t* occ = host.data() + (size_t)i * d.st_stride + d.st_occ;
+    const uint8_t* occ = host.data() + (size_t)i * d.L.st_stride + d.L.st_occ;
     for (int r = 0; r < 64; ++r) {
       uint64_t v = 0;
       if (e->wide) v = reinterpret_cast<const uint64_t*>(occ)[r];
@@ -571,5 +633,51 @@ int pcb_get_occupancy(pcb_env_t* e, uint64_t* h_rows, void* stream) {
 }
 
 int64_t pcb_launch_count(pcb_env_t* e) { return e ? e->launches : 0; }
+
+int pcb_rollout_random(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_actions_log, void* stream) {
+  int rc = ready(e);
+  if (rc) return rc;
+  if (n_steps < 0) return fail(PCB_ERR_INVALID, "n_steps must be >= 0");
+  if (n_steps == 0) return 0;
+  const size_t per = (size_t)e->n_envs * (e->d.kind == 0 ? 2 : 3);
+  // the first action comes from the stand-alone sampler; every step kernel then also
+  // draws the action of the following step (same Philox counter as the sampler would use)
+  int32_t* cur = d_actions_log ? d_actions_log : e->d_actions;
+  rc = pcb_sample_random_actions(e, seed, cur, stream);
+  if (rc) return rc;
+  for (int t = 0; t < n_steps; ++t) {
+    int32_t* nxt = nullptr;
+    if (t + 1 < n_steps)
+      nxt = d_actions_log ? d_actions_log + (size_t)(t + 1) * per
+                          : (cur == e->d_actions ? e->d_actions2 : e->d_actions);
+    rc = step_impl(e, cur, PCB_ACTION_TUPLE, seed, nxt, stream);
+    if (rc) return rc;
+    cur = nxt;
+  }
+  return 0;
+}
+
+int pcb_enable_kernel_timing(pcb_env_t* e, int on) {
+  if (!e) return fail(PCB_ERR_INVALID, "env is NULL");
+  e->timing = on != 0;
+  return 0;
+}
+
+int pcb_kernel_times(pcb_env_t* e, double ms[4], int64_t launches[4]) {
+  if (!e || !ms || !launches) return fail(PCB_ERR_INVALID, "NULL argument");
+  CU(cudaSetDevice(e->device));
+  for (int i = 0; i < 4; ++i) { ms[i] = 0.0; launches[i] = 0; }
+  for (auto& t : e->timed) {
+    CU(cudaEventSynchronize(t.b));
+    float v = 0.f;
+    CU(cudaEventElapsedTime(&v, t.a, t.b));
+    ms[t.id] += v;
+    launches[t.id] += 1;
+    cudaEventDestroy(t.a);
+    cudaEventDestroy(t.b);
+  }
+  e->timed.clear();
+  return 0;
+}
 
 }  // extern "C"

@@ -224,29 +224,28 @@ template <typename T>
 __device__ __forceinline__ void beam_route(const Dims& d, const Env<T>& e, const RouteScratch& rs,
                                            int lane, int n_pins, int n_nets, int& crossings,
                                            double& wl) {
-  int cnt = 0;
-  for (int s = 0; s < n_pins; ++s) {
-    const int sn = rs.nxt[s];
-    if (sn == 0xFFFF) continue;
-    const double sx1 = rs.px[s], sy1 = rs.py[s], sx2 = rs.px[sn], sy2 = rs.py[sn];
-    const int snet = e.pins[s].net;
-    for (int t = rs.net_off[snet + 1] + lane; t < n_pins; t += 32) {
-      const int tn = rs.nxt[t];
-      if (tn == 0xFFFF) continue;
-      if (segments_cross(sx1, sy1, sx2, sy2, rs.px[t], rs.py[t], rs.px[tn], rs.py[tn])) ++cnt;
+  for (int q = lane; q < n_pins; q += 32) {
+    const int nx = rs.nxt[q];
+    double x2 = 0.0, y2 = 0.0, len = -1.0;
+    uint32_t box = kNoBox;
+    if (nx != 0xFFFF) {
+      const double x1 = (double)rs.px[q], y1 = (double)rs.py[q];
+      x2 = (double)rs.px[nx]; y2 = (double)rs.py[nx];
+      box = make_box(x1, y1, x2, y2);
+      len = norm2(x1 - x2, y1 - y2, d.norm_fma);
     }
+    rs.x2[q] = x2; rs.y2[q] = y2; rs.box[q] = box; rs.dist[q] = len;
   }
-  for (int off = 16; off; off >>= 1) cnt += __shfl_xor_sync(kFull, cnt, off);
-  crossings = cnt;
+  __syncwarp();
+  crossings = count_crossings<T>(e, rs, lane, n_pins);
   // find_wirelength: nets in order, segments in path order, sequential float64 sum
   double acc = 0.0;
   if (lane == 0) {
     for (int net = 0; net < n_nets; ++net) {
       int q = rs.start[net];
       while (rs.nxt[q] != 0xFFFF) {
-        int nx = rs.nxt[q];
-        acc += norm2((double)(rs.px[q] - rs.px[nx]), (double)(rs.py[q] - rs.py[nx]), d.norm_fma);
-        q = nx;
+        acc += rs.dist[q];
+        q = rs.nxt[q];
       }
     }
   }

@@ -3,13 +3,14 @@
 // One warp owns one environment.  The occupancy grid is a bitboard, one word per
 // grid row, lane r holding row r (and row r+32 for grids taller than 32).  The
 // valid-position mask of a (ph, pw) footprint is a sliding-window AND over the
-// free bits: pw-1 shift/ANDs inside the row word, ph-1 warp shuffles across rows.
-// Nothing here is a dense contraction, so no tensor cores: the kernels are bound
-// by the HBM write-out of the observation slab (bit -> byte expansion + 16-byte
-// coalesced stores).  Compiled with -fmad=false: every float64 product and sum
-// below is individually rounded like the reference's Python/numpy arithmetic;
-// the one fused multiply-add of the reference (numpy ddot inside linalg.norm) is
-// written explicitly.
+// free bits: log2(pw) shift/ANDs inside the row word, log2(ph) warp shuffles across
+// rows.  Nothing here is a dense contraction, so no tensor cores: the kernels are
+// bound by the HBM write-out of the observation slab (bit -> byte expansion in
+// registers + 16-byte coalesced stores) and by instruction issue, which is why the
+// canonical shapes are compiled with every dimension as a constant (FixedShape).
+// Compiled with -fmad=false: every float64 product and sum below is individually
+// rounded like the reference's Python/numpy arithmetic; the one fused multiply-add
+// of the reference (numpy ddot inside linalg.norm) is written explicitly.
 #ifndef PCB_KERNELS_CUH_
 #define PCB_KERNELS_CUH_
 
@@ -21,6 +22,57 @@
 namespace pcb {
 
 constexpr unsigned kFull = 0xffffffffu;
+
+// ---------------------------------------------------------------------------
+// shapes: every dimension either a compile-time constant or read from Dims
+// ---------------------------------------------------------------------------
+#define PCB_LAYOUT_FIELDS(X)                                                                   \
+  X(O) X(P) X(F) X(st_comps) X(st_pins) X(st_occ) X(st_stride) X(rec_comps) X(rec_pins)        \
+  X(rec_stride) X(grid_b) X(mask_b) X(feat_n) X(pnum_n) X(pcat_n) X(pgrid_b) X(cgrid_b)        \
+  X(sm_mrow) X(sm_stage) X(sm_scr) X(sm_stride)
+
+template <int KIND, int HH, int WW, int CC, int MH, int MW, int KK, int MAXPINS>
+struct FixedShape {
+  static constexpr bool fixed = true;
+  static constexpr Layout LL = make_layout(KIND, HH, WW, CC, MH, MW, KK, MAXPINS);
+  __device__ __forceinline__ explicit FixedShape(const Dims&) {}
+  __device__ __forceinline__ constexpr int kind() const { return KIND; }
+  __device__ __forceinline__ constexpr int H() const { return HH; }
+  __device__ __forceinline__ constexpr int W() const { return WW; }
+  __device__ __forceinline__ constexpr int C() const { return CC; }
+  __device__ __forceinline__ constexpr int K() const { return KK; }
+  __device__ __forceinline__ constexpr int mh() const { return MH; }
+  __device__ __forceinline__ constexpr int mw() const { return MW; }
+  __device__ __forceinline__ constexpr int max_pins() const { return MAXPINS; }
+#define X(f) \
+  __device__ __forceinline__ constexpr int f() const { return LL.f; }
+  PCB_LAYOUT_FIELDS(X)
+#undef X
+};
+
+struct DynShape {
+  static constexpr bool fixed = false;
+  const Dims& d;
+  __device__ __forceinline__ explicit DynShape(const Dims& dd) : d(dd) {}
+  __device__ __forceinline__ int kind() const { return d.kind; }
+  __device__ __forceinline__ int H() const { return d.H; }
+  __device__ __forceinline__ int W() const { return d.W; }
+  __device__ __forceinline__ int C() const { return d.C; }
+  __device__ __forceinline__ int K() const { return d.K; }
+  __device__ __forceinline__ int mh() const { return d.mh; }
+  __device__ __forceinline__ int mw() const { return d.mw; }
+  __device__ __forceinline__ int max_pins() const { return d.max_pins; }
+#define X(f) \
+  __device__ __forceinline__ int f() const { return d.L.f; }
+  PCB_LAYOUT_FIELDS(X)
+#undef X
+};
+
+// the canonical configurations of BASELINE.md section 2
+using ShapeB = FixedShape<1, 16, 16, 6, 4, 4, 0, 0>;
+using ShapeC = FixedShape<2, 32, 32, 10, 4, 4, 6, 30>;
+using ShapeD = FixedShape<3, 32, 32, 10, 4, 4, 6, 30>;
+using ShapeE = FixedShape<2, 64, 64, 32, 4, 4, 17, 96>;
 
 // ---------------------------------------------------------------------------
 // small helpers
@@ -41,11 +93,28 @@ __device__ __forceinline__ uint4 spread16(uint32_t b) {
 }
 
 template <typename T>
-__device__ __forceinline__ int popc_t(T v);
-template <>
-__device__ __forceinline__ int popc_t<uint32_t>(uint32_t v) { return __popc(v); }
-template <>
-__device__ __forceinline__ int popc_t<uint64_t>(uint64_t v) { return __popcll(v); }
+__device__ __forceinline__ int popc_t(T v) {
+  if constexpr (sizeof(T) == 8) return __popcll((unsigned long long)v);
+  else return __popc((unsigned)v);
+}
+
+template <typename T>
+__device__ __forceinline__ int ffs_t(T v) {  // index of the lowest set bit, v != 0
+  if constexpr (sizeof(T) == 8) return __ffsll((long long)v) - 1;
+  else return __ffs((int)v) - 1;
+}
+
+// position of the (n+1)-th set bit (n counted from 0); garbage when v has fewer bits
+template <typename T>
+__device__ __forceinline__ int nth_bit(T v, int n) {
+  if constexpr (sizeof(T) == 8) {
+    unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
+    int cl = __popc(lo);
+    return n < cl ? (int)__fns(lo, 0, n + 1) : 32 + (int)__fns(hi, 0, n - cl + 1);
+  } else {
+    return (int)__fns((unsigned)v, 0, n + 1);
+  }
+}
 
 // smem -> global copy of one environment's slice of a tensor, widest store the
 // alignment allows (16 B when the per-env size is a multiple of 16).
@@ -71,6 +140,12 @@ __device__ __forceinline__ void zero_smem(void* p, int nbytes, int lane) {  // n
   for (int i = lane; i < (nbytes >> 4); i += 32) d[i] = make_uint4(0, 0, 0, 0);
 }
 
+__device__ __forceinline__ void copy16(void* dst, const void* src, int nbytes, int lane) {
+  const uint4* s = reinterpret_cast<const uint4*>(src);
+  uint4* d = reinterpret_cast<uint4*>(dst);
+  for (int i = lane; i < (nbytes >> 4); i += 32) d[i] = s[i];
+}
+
 // ---------------------------------------------------------------------------
 // bitboard: footprint mask (reference: compute_action_mask_orientation,
 // dummy_env_rectangular.py:526-567 / dummy_env_rectangular_pin.py:1808-1851;
@@ -78,64 +153,128 @@ __device__ __forceinline__ void zero_smem(void* p, int nbytes, int lane) {  // n
 //   out[r] bit j = 1  iff  r + ph <= H, j + pw <= W and rows r..r+ph-1,
 //   columns j..j+pw-1 are all free.
 // ---------------------------------------------------------------------------
+// rows shifted up by dlt: result[r] = v[r + dlt], zero past the last row
 template <int RPL, typename T>
-__device__ __forceinline__ void footprint_mask(const T (&occ)[RPL], int ph, int pw, int H, int W,
-                                               int lane, T (&out)[RPL]) {
-  T e[RPL];
-#pragma unroll
-  for (int k = 0; k < RPL; ++k) {
-    int row = lane + 32 * k;
-    T fr = row < H ? (T)(~occ[k] & low_mask<T>(W)) : T(0);
-    T acc = fr;
-    for (int dlt = 1; dlt < pw; ++dlt) acc &= fr >> dlt;  // zeros shift in above column W-1
-    e[k] = acc;
-    out[k] = acc;
-  }
-  for (int dlt = 1; dlt < ph; ++dlt) {
-    int src = (lane + dlt) & 31;
-    int hop = (lane + dlt) >> 5;  // how many 32-row slots the source row is ahead
+__device__ __forceinline__ void rows_ahead(const T (&v)[RPL], int dlt, int lane, T (&out)[RPL]) {
+  if constexpr (RPL == 1) {
+    T t = __shfl_down_sync(kFull, v[0], dlt);
+    out[0] = lane + dlt < 32 ? t : T(0);
+  } else {
+    int src = (lane + dlt) & 31, hop = (lane + dlt) >> 5;
     T got[RPL];
 #pragma unroll
-    for (int k = 0; k < RPL; ++k) got[k] = __shfl_sync(kFull, e[k], src);
+    for (int k = 0; k < RPL; ++k) got[k] = __shfl_sync(kFull, v[k], src);
 #pragma unroll
     for (int k = 0; k < RPL; ++k) {
-      T v = T(0);
+      T r = T(0);
 #pragma unroll
       for (int kk = 0; kk < RPL; ++kk)
-        if (k + hop == kk) v = got[kk];
-      out[k] &= v;  // rows past the last slot count as blocked
+        if (k + hop == kk) r = got[kk];
+      out[k] = r;
     }
   }
 }
 
-// bit rows (in shared memory, one word per row) -> H*W bytes of 0/1 in global memory.
-// dup_off != 0 writes a second copy at dst + dup_off (orientations 2,3 of the pin
-// env repeat 0,1: dummy_env_rectangular_pin.py:1868-1869).
-template <typename T>
-__device__ __forceinline__ void write_bits(uint8_t* dst, const T* rows, int H, int W, int lane,
-                                           int dup_off) {
-  if ((W & 15) == 0) {
-    const int cpr = W >> 4;  // 16-byte chunks per row: 1..4
-    const int n = H * cpr;
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
-    uint4* e4 = reinterpret_cast<uint4*>(dst + dup_off);
-    for (int q = lane; q < n; q += 32) {
-      int row, part;
-      if (cpr == 2) { row = q >> 1; part = q & 1; }
-      else if (cpr == 4) { row = q >> 2; part = q & 3; }
-      else if (cpr == 1) { row = q; part = 0; }
-      else { row = q / 3; part = q - 3 * row; }
-      uint4 v = spread16((uint32_t)(rows[row] >> (16 * part)) & 0xffffu);
-      d4[q] = v;
-      if (dup_off) e4[q] = v;
+template <int RPL, typename T>
+__device__ __forceinline__ void footprint_mask(const T (&occ)[RPL], int ph, int pw, int H, int W,
+                                               int lane, T (&out)[RPL]) {
+#pragma unroll
+  for (int k = 0; k < RPL; ++k) {
+    int row = lane + 32 * k;
+    T v = row < H ? (T)(~occ[k] & low_mask<T>(W)) : T(0);
+    // AND of v >> 0 .. v >> (pw-1) by doubling; zeros shift in above column W-1
+    int s = 1;
+    while (2 * s <= pw) { v &= v >> s; s <<= 1; }
+    if (s < pw) v &= v >> (pw - s);
+    out[k] = v;
+  }
+  int s = 1;
+  T t[RPL];
+  while (2 * s <= ph) {
+    rows_ahead<RPL, T>(out, s, lane, t);
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) out[k] &= t[k];
+    s <<= 1;
+  }
+  if (s < ph) {
+    rows_ahead<RPL, T>(out, ph - s, lane, t);
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) out[k] &= t[k];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// bit rows -> H*W bytes of 0/1 in global memory.  dup_off != 0 writes a second copy
+// at dst + dup_off (orientations 2,3 of the pin env repeat 0,1: pin:1868-1869).
+// Fixed 32x32 / 64x64 / 16x16 boards go register -> shuffle -> 16-byte store, every
+// store instruction covering 512 contiguous bytes; other shapes read the rows from
+// shared memory.
+// ---------------------------------------------------------------------------
+template <typename S>
+struct BoardPath {
+  static constexpr bool fast = false;
+};
+template <int KIND, int CC, int MH, int MW, int KK, int MP>
+struct BoardPath<FixedShape<KIND, 32, 32, CC, MH, MW, KK, MP>> { static constexpr bool fast = true; };
+template <int KIND, int CC, int MH, int MW, int KK, int MP>
+struct BoardPath<FixedShape<KIND, 64, 64, CC, MH, MW, KK, MP>> { static constexpr bool fast = true; };
+template <int KIND, int CC, int MH, int MW, int KK, int MP>
+struct BoardPath<FixedShape<KIND, 16, 16, CC, MH, MW, KK, MP>> { static constexpr bool fast = true; };
+
+template <int RPL, typename T, typename S>
+__device__ __forceinline__ void write_board(const S& sh, uint8_t* dst, const T (&regs)[RPL],
+                                            const T* rows, int lane, int dup_off) {
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+  uint4* e4 = reinterpret_cast<uint4*>(dst + dup_off);
+  if constexpr (BoardPath<S>::fast) {
+    if constexpr (sizeof(T) == 4 && RPL == 1) {
+      if (sh.W() == 32) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t w = __shfl_sync(kFull, regs[0], (lane >> 1) + 16 * half);
+          uint4 v = spread16((w >> (16 * (lane & 1))) & 0xffffu);
+          d4[half * 32 + lane] = v;
+          if (dup_off) e4[half * 32 + lane] = v;
+        }
+      } else {  // 16x16: one 16-byte chunk per row
+        if (lane < 16) {
+          uint4 v = spread16((uint32_t)regs[0] & 0xffffu);
+          d4[lane] = v;
+          if (dup_off) e4[lane] = v;
+        }
+      }
+    } else {  // 64x64: 4 chunks per row, 256 chunks
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        T w = __shfl_sync(kFull, regs[i >> 2], (i & 3) * 8 + (lane >> 2));
+        uint4 v = spread16((uint32_t)(w >> (16 * (lane & 3))) & 0xffffu);
+        d4[i * 32 + lane] = v;
+        if (dup_off) e4[i * 32 + lane] = v;
+      }
     }
   } else {
-    const int n = H * W;
-    for (int b = lane; b < n; b += 32) {
-      int row = b / W, col = b - row * W;
-      uint8_t v = (uint8_t)((rows[row] >> col) & T(1));
-      dst[b] = v;
-      if (dup_off) dst[b + dup_off] = v;
+    const int H = sh.H(), W = sh.W();
+    if ((W & 15) == 0) {
+      const int cpr = W >> 4;  // 16-byte chunks per row: 1..4
+      const int n = H * cpr;
+      for (int q = lane; q < n; q += 32) {
+        int row, part;
+        if (cpr == 2) { row = q >> 1; part = q & 1; }
+        else if (cpr == 4) { row = q >> 2; part = q & 3; }
+        else if (cpr == 1) { row = q; part = 0; }
+        else { row = q / 3; part = q - 3 * row; }
+        uint4 v = spread16((uint32_t)(rows[row] >> (16 * part)) & 0xffffu);
+        d4[q] = v;
+        if (dup_off) e4[q] = v;
+      }
+    } else {
+      const int n = H * W;
+      for (int b = lane; b < n; b += 32) {
+        int row = b / W, col = b - row * W;
+        uint8_t v = (uint8_t)((rows[row] >> col) & T(1));
+        dst[b] = v;
+        if (dup_off) dst[b + dup_off] = v;
+      }
     }
   }
 }
@@ -151,110 +290,168 @@ struct Env {
   CompRec* comps;
   PinRec* pins;
   T* occ;      // 32*RPL words
-  T* mrow;     // [2][32*RPL] mask rows of orientation 0 / 1
+  T* mrow;     // [2][32*RPL] mask rows of orientation 0 / 1 (generic board path only)
   uint8_t* stage;
   uint8_t* scr;
-  __device__ __forceinline__ Env(uint8_t* base, const Dims& d, int rows)
+  template <typename S>
+  __device__ __forceinline__ Env(uint8_t* base, const S& sh)
       : sm(base),
         hdr(reinterpret_cast<EnvHdr*>(base)),
         dyn(reinterpret_cast<EnvDyn*>(base + 16)),
-        comps(reinterpret_cast<CompRec*>(base + d.st_comps)),
-        pins(reinterpret_cast<PinRec*>(base + d.st_pins)),
-        occ(reinterpret_cast<T*>(base + d.st_occ)),
-        mrow(reinterpret_cast<T*>(base + d.sm_mrow)),
-        stage(base + d.sm_stage),
-        scr(base + d.sm_scr) {}
+        comps(reinterpret_cast<CompRec*>(base + sh.st_comps())),
+        pins(reinterpret_cast<PinRec*>(base + sh.st_pins())),
+        occ(reinterpret_cast<T*>(base + sh.st_occ())),
+        mrow(reinterpret_cast<T*>(base + sh.sm_mrow())),
+        stage(base + sh.sm_stage()),
+        scr(base + sh.sm_scr()) {}
 };
 
-__device__ __forceinline__ void load_state(uint8_t* sm, const uint8_t* g, int nbytes, int lane) {
-  const uint4* s = reinterpret_cast<const uint4*>(g);
-  uint4* d = reinterpret_cast<uint4*>(sm);
-  for (int i = lane; i < (nbytes >> 4); i += 32) d[i] = s[i];
+// ---------------------------------------------------------------------------
+// K7: the random policy of agent/random/random_policy_*.py:11-58 -- uniform over
+// np.argwhere(action_mask == 1), i.e. over the set bits of the mask bitboards in
+// (orientation, row, column) order.  Philox4x32-10 keyed by the seed, counter =
+// (env, step).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t philox_u32(uint64_t seed, uint32_t c0, uint32_t c1,
+                                               uint32_t c2) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = 0x5043422du;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
+    uint32_t y0 = hi1 ^ x1 ^ k0, y1 = lo1, y2 = hi0 ^ x3 ^ k1, y3 = lo0;
+    x0 = y0; x1 = y1; x2 = y2; x3 = y3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return x0;
+}
+
+template <int RPL, typename T, typename S>
+__device__ __forceinline__ void sample_action(const S& sh, const T (&m0)[RPL], const T (&m1)[RPL],
+                                              uint64_t seed, int env, uint64_t step_no, int lane,
+                                              int32_t* out) {
+  int c0 = 0, c1 = 0;
+#pragma unroll
+  for (int k = 0; k < RPL; ++k) { c0 += popc_t<T>(m0[k]); c1 += popc_t<T>(m1[k]); }
+  const int tot0 = __reduce_add_sync(kFull, c0), tot1 = __reduce_add_sync(kFull, c1);
+  const int per_pair = tot0 + tot1;
+  const int O = sh.O();
+  const int total = O == 4 ? 2 * per_pair : (O == 2 ? per_pair : tot0);
+  int ao = 0, ax = 0, ay = 0;
+  if (total > 0) {
+    uint32_t r = philox_u32(seed, (uint32_t)env, (uint32_t)step_no, (uint32_t)(step_no >> 32));
+    int kth = (int)__umulhi(r, (uint32_t)total);  // uniform in [0, total)
+    int obase = 0;
+    if (O == 4 && kth >= per_pair) { kth -= per_pair; obase = 2; }
+    const bool second = kth >= tot0;
+    if (second) kth -= tot0;
+    int found_row = -1, found_col = 0;
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) {  // rows in order: slot 0 lanes 0..31, then slot 1
+      const T bits = second ? m1[k] : m0[k];
+      const int c = popc_t<T>(bits);
+      int incl = c;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        int v = __shfl_up_sync(kFull, incl, off);
+        if (lane >= off) incl += v;
+      }
+      const int slot_total = __shfl_sync(kFull, incl, 31);
+      const int excl = incl - c;
+      const bool mine = found_row < 0 && kth >= excl && kth < incl;
+      const unsigned who = __ballot_sync(kFull, mine);
+      const int col = nth_bit<T>(bits, kth - excl);
+      if (who && found_row < 0) {
+        const int src = __ffs(who) - 1;
+        found_col = __shfl_sync(kFull, col, src);
+        found_row = src + 32 * k;
+      }
+      if (found_row < 0) kth -= slot_total;
+    }
+    ao = obase + (second ? 1 : 0); ax = found_row; ay = found_col;
+  }
+  if (lane == 0) {
+    if (sh.kind() == 0) { out[2 * env] = ax; out[2 * env + 1] = ay; }
+    else { out[3 * env] = ao; out[3 * env + 1] = ax; out[3 * env + 2] = ay; }
+  }
 }
 
 // ---------------------------------------------------------------------------
 // observation write-out (everything the reference copies into the obs dict:
 // rect:410-416, pin:1680-1687, spatial:1633-1644; layout SURVEY.md Appendix C)
 // ---------------------------------------------------------------------------
-template <int RPL, typename T>
-__device__ __forceinline__ void write_obs(const Params& p, Env<T>& e, int env, int lane,
-                                          const T (&m0)[RPL], const T (&m1)[RPL]) {
-  const Dims& d = p.d;
-  const int rows = 32 * RPL;
+template <int RPL, typename T, typename S>
+__device__ __forceinline__ void write_obs(const S& sh, const Params& p, Env<T>& e, int env,
+                                          int lane, const T (&occ)[RPL], const T (&m0)[RPL],
+                                          const T (&m1)[RPL]) {
+  constexpr int rows = 32 * RPL;
+  if constexpr (!BoardPath<S>::fast) {
 #pragma unroll
-  for (int k = 0; k < RPL; ++k) {
-    e.mrow[lane + 32 * k] = m0[k];
-    e.mrow[rows + lane + 32 * k] = m1[k];
+    for (int k = 0; k < RPL; ++k) {
+      e.occ[lane + 32 * k] = occ[k];
+      e.mrow[lane + 32 * k] = m0[k];
+      e.mrow[rows + lane + 32 * k] = m1[k];
+    }
+    __syncwarp();
   }
-  __syncwarp();
-  const int HW = d.H * d.W;
-  write_bits<T>(p.out.grid + (size_t)env * d.grid_b, e.occ, d.H, d.W, lane, 0);
-  uint8_t* mk = p.out.mask + (size_t)env * d.mask_b;
-  write_bits<T>(mk, e.mrow, d.H, d.W, lane, d.O == 4 ? 2 * HW : 0);
-  if (d.O >= 2) write_bits<T>(mk + HW, e.mrow + rows, d.H, d.W, lane, d.O == 4 ? 2 * HW : 0);
-  if (d.kind == 0) return;
+  const int HW = sh.H() * sh.W();
+  const int O = sh.O();
+  write_board<RPL, T, S>(sh, p.out.grid + (size_t)env * sh.grid_b(), occ, e.occ, lane, 0);
+  uint8_t* mk = p.out.mask + (size_t)env * sh.mask_b();
+  write_board<RPL, T, S>(sh, mk, m0, e.mrow, lane, O == 4 ? 2 * HW : 0);
+  if (O >= 2) write_board<RPL, T, S>(sh, mk + HW, m1, e.mrow + rows, lane, O == 4 ? 2 * HW : 0);
+  const int kind = sh.kind();
+  if (kind == 0) return;
 
+  const int C = sh.C(), F = sh.F();
   const int n_comp = e.hdr->n_comp, cur = e.hdr->cur, n_pins = e.hdr->n_pins;
-  const double inv_area_den = (double)(d.H * d.W);
 
   // all_components_feature: [h, w, x|-1, y|-1, h*w/(H*W)] (+ pin ids, spatial)
-  float* feat = p.out.feat + (size_t)env * d.feat_n;
-  if (d.kind != 3) {
-    for (int i = lane; i < d.feat_n; i += 32) {
-      int c = i / 5, f = i - 5 * c;
-      float v = 0.f;
-      if (c < n_comp) {
-        CompRec r = e.comps[c];
-        if (f == 0) v = (float)r.h;
-        else if (f == 1) v = (float)r.w;
-        else if (f == 2) v = r.x == 0xFF ? -1.f : (float)r.x;
-        else if (f == 3) v = r.y == 0xFF ? -1.f : (float)r.y;
-        else v = (float)((double)(r.h * r.w) / inv_area_den);
-      }
-      feat[i] = v;
+  float* feat = p.out.feat + (size_t)env * sh.feat_n();
+  float* fdst = kind == 3 ? reinterpret_cast<float*>(e.stage) : feat;
+  for (int i = lane; i < sh.feat_n(); i += 32) {
+    int c = i / F, f = i - F * c;
+    float v = 0.f;
+    if (c < n_comp) {
+      CompRec r = e.comps[c];
+      if (f == 0) v = (float)r.h;
+      else if (f == 1) v = (float)r.w;
+      else if (f == 2) v = r.x == 0xFF ? -1.f : (float)r.x;
+      else if (f == 3) v = r.y == 0xFF ? -1.f : (float)r.y;
+      else if (f == 4) v = p.ratio_lut[r.h * r.w];
+      else v = -1.f;
     }
-  } else {
-    float* st = reinterpret_cast<float*>(e.stage);
-    for (int i = lane; i < d.feat_n; i += 32) {
-      int c = i / d.F, f = i - d.F * c;
-      float v = 0.f;
-      if (c < n_comp) {
-        CompRec r = e.comps[c];
-        if (f == 0) v = (float)r.h;
-        else if (f == 1) v = (float)r.w;
-        else if (f == 2) v = r.x == 0xFF ? -1.f : (float)r.x;
-        else if (f == 3) v = r.y == 0xFF ? -1.f : (float)r.y;
-        else if (f == 4) v = (float)((double)(r.h * r.w) / inv_area_den);
-        else v = -1.f;
-      }
-      st[i] = v;
-    }
+    fdst[i] = v;
+  }
+  if (kind == 3) {
     __syncwarp();
     for (int q = lane; q < n_pins; q += 32) {
       PinRec pr = e.pins[q];
-      st[pr.comp * d.F + 5 + pr.rank] = (float)pr.pin_id;
+      fdst[pr.comp * F + 5 + pr.rank] = (float)pr.pin_id;
     }
     __syncwarp();
-    copy_out(feat, st, d.feat_n * 4, lane);
+    copy_out(feat, fdst, sh.feat_n() * 4, lane);
     __syncwarp();
   }
 
   // placement_mask / component_mask
-  for (int c = lane; c < d.C; c += 32) {
-    if (d.kind == 1) {
-      p.out.place_mask[(size_t)env * d.C + c] = c < cur ? 1 : 0;       // rect:284
-      p.out.comp_mask[(size_t)env * d.C + c] = c < n_comp ? 1 : 0;     // rect:296-298
+  for (int c = lane; c < C; c += 32) {
+    if (kind == 1) {
+      p.out.place_mask[(size_t)env * C + c] = c < cur ? 1 : 0;       // rect:284
+      p.out.comp_mask[(size_t)env * C + c] = c < n_comp ? 1 : 0;     // rect:296-298
     } else {
       uint8_t v = c >= n_comp ? 0 : (c < cur ? 2 : (c == cur ? 3 : 1));  // pin:1577-1579, 1649-1657
-      p.out.place_mask[(size_t)env * d.C + c] = v;
+      p.out.place_mask[(size_t)env * C + c] = v;
     }
   }
-  if (d.kind == 1) return;
+  if (kind == 1) return;
 
   // all_pins_num_feature / all_pins_cat_feature (pin:1521-1542, spatial:1469-1485)
+  const int pnum_n = sh.pnum_n(), pcat_n = sh.pcat_n();
   int16_t* snum = reinterpret_cast<int16_t*>(e.stage);
-  int16_t* scat = snum + d.pnum_n;
-  zero_smem(e.stage, ((d.pnum_n + d.pcat_n) * 2 + 15) & ~15, lane);
+  int16_t* scat = snum + pnum_n;
+  zero_smem(e.stage, ((pnum_n + pcat_n) * 2 + 15) & ~15, lane);
   __syncwarp();
   for (int q = lane; q < n_pins; q += 32) {
     PinRec pr = e.pins[q];
@@ -262,31 +459,36 @@ __device__ __forceinline__ void write_obs(const Params& p, Env<T>& e, int env, i
     CompRec r = e.comps[pr.comp];
     int ax = r.x == 0xFF ? -1 : r.x + pr.rx;
     int ay = r.x == 0xFF ? -1 : r.y + pr.ry;
-    int row = d.kind == 3 ? pr.pin_id : pr.comp * d.P + pr.pin_id;
-    int16_t* nr = snum + row * 4;
-    nr[0] = pr.rx; nr[1] = pr.ry; nr[2] = (int16_t)ax; nr[3] = (int16_t)ay;
-    if (d.kind == 3) { scat[row * 2] = pr.net; scat[row * 2 + 1] = pr.comp; }
-    else scat[row] = pr.net;
+    int row = kind == 3 ? pr.pin_id : pr.comp * sh.P() + pr.pin_id;
+    // one 8-byte store: [rel_x, rel_y, abs_x, abs_y] as int16
+    uint2 v = make_uint2((uint32_t)pr.rx | ((uint32_t)pr.ry << 16),
+                         ((uint32_t)ax & 0xffffu) | ((uint32_t)ay << 16));
+    *reinterpret_cast<uint2*>(snum + row * 4) = v;
+    if (kind == 3)
+      *reinterpret_cast<uint32_t*>(scat + row * 2) = (uint32_t)pr.net | ((uint32_t)pr.comp << 16);
+    else
+      scat[row] = pr.net;
   }
-  if (d.kind == 3 && lane == 0) { scat[d.pcat_n - 2] = -1; scat[d.pcat_n - 1] = -1; }
+  if (kind == 3 && lane == 0) { scat[pcat_n - 2] = -1; scat[pcat_n - 1] = -1; }
   __syncwarp();
-  copy_out(p.out.pnum + (size_t)env * d.pnum_n, snum, d.pnum_n * 2, lane);
-  copy_out(p.out.pcat + (size_t)env * d.pcat_n, scat, d.pcat_n * 2, lane);
+  copy_out(p.out.pnum + (size_t)env * pnum_n, snum, pnum_n * 2, lane);
+  copy_out(p.out.pcat + (size_t)env * pcat_n, scat, pcat_n * 2, lane);
   __syncwarp();
-  if (d.kind != 3) return;
+  if (kind != 3) return;
 
   // pin_grid (spatial:1663-1675): channel 0 = occupied cell without a pin,
   // channel net+1 = placed pin of that net.
-  zero_smem(e.stage, (d.pgrid_b + 15) & ~15, lane);
+  const int K = sh.K(), W = sh.W();
+  zero_smem(e.stage, (sh.pgrid_b() + 15) & ~15, lane);
   __syncwarp();
 #pragma unroll
   for (int k = 0; k < RPL; ++k) {
     int row = lane + 32 * k;
-    T bits = row < d.H ? e.occ[row] : T(0);
+    T bits = row < sh.H() ? occ[k] : T(0);
     while (bits) {
-      int j = sizeof(T) == 8 ? __ffsll((long long)bits) - 1 : __ffs((int)bits) - 1;
+      int j = ffs_t<T>(bits);
       bits &= bits - 1;
-      e.stage[(row * d.W + j) * d.K] = 1;
+      e.stage[(row * W + j) * K] = 1;
     }
   }
   __syncwarp();
@@ -294,46 +496,51 @@ __device__ __forceinline__ void write_obs(const Params& p, Env<T>& e, int env, i
     PinRec pr = e.pins[q];
     CompRec r = e.comps[pr.comp];
     if (r.x == 0xFF) continue;
-    uint8_t* cell = e.stage + ((r.x + pr.rx) * d.W + (r.y + pr.ry)) * d.K;
+    uint8_t* cell = e.stage + ((r.x + pr.rx) * W + (r.y + pr.ry)) * K;
     cell[0] = 0;
     cell[pr.net + 1] = 1;
   }
   __syncwarp();
-  copy_out(p.out.pgrid + (size_t)env * d.pgrid_b, e.stage, d.pgrid_b, lane);
+  copy_out(p.out.pgrid + (size_t)env * sh.pgrid_b(), e.stage, sh.pgrid_b(), lane);
   __syncwarp();
 
   // component_grid (spatial:1677-1697): drawn at reset from the UN-rotated pin
   // coordinates, i.e. from the bank record, and constant during the episode.
-  zero_smem(e.stage, (d.cgrid_b + 15) & ~15, lane);
+  zero_smem(e.stage, (sh.cgrid_b() + 15) & ~15, lane);
   __syncwarp();
-  const int cells = d.mh * d.mw;
-  for (int i = lane; i < n_comp * cells; i += 32) e.stage[i * d.K] = 1;
+  const int cells = sh.mh() * sh.mw();
+  for (int i = lane; i < n_comp * cells; i += 32) e.stage[i * K] = 1;
   __syncwarp();
-  const PinRec* bp = reinterpret_cast<const PinRec*>(p.bank + (size_t)e.hdr->slot * d.rec_stride +
-                                                     d.rec_pins);
+  const PinRec* bp = reinterpret_cast<const PinRec*>(
+      p.bank + (size_t)e.hdr->slot * sh.rec_stride() + sh.rec_pins());
   for (int q = lane; q < n_pins; q += 32) {
     PinRec pr = bp[q];
-    e.stage[((pr.comp * d.mh + pr.rx) * d.mw + pr.ry) * d.K + pr.net + 1] = 1;
+    e.stage[((pr.comp * sh.mh() + pr.rx) * sh.mw() + pr.ry) * K + pr.net + 1] = 1;
   }
   __syncwarp();
-  copy_out(p.out.cgrid + (size_t)env * d.cgrid_b, e.stage, d.cgrid_b, lane);
+  copy_out(p.out.cgrid + (size_t)env * sh.cgrid_b(), e.stage, sh.cgrid_b(), lane);
   __syncwarp();
 }
 
 // Mask rows of the component to place next (both orientations); zero when none is left
 // (rect:399-402, pin:1663-1666).  Returns true when at least one position is valid.
-template <int RPL, typename T>
-__device__ __forceinline__ bool next_masks(const Dims& d, const Env<T>& e, const T (&occ)[RPL],
-                                           int cur, int n_comp, int lane, T (&m0)[RPL],
-                                           T (&m1)[RPL]) {
+template <int RPL, typename T, typename S>
+__device__ __forceinline__ bool next_masks(const S& sh, const Dims& d, const Env<T>& e,
+                                           const T (&occ)[RPL], int cur, int n_comp, int lane,
+                                           T (&m0)[RPL], T (&m1)[RPL]) {
 #pragma unroll
   for (int k = 0; k < RPL; ++k) { m0[k] = T(0); m1[k] = T(0); }
-  if (d.kind == 0) {
-    footprint_mask<RPL, T>(occ, d.sq_n, d.sq_n, d.H, d.W, lane, m0);
+  if (sh.kind() == 0) {
+    footprint_mask<RPL, T>(occ, d.sq_n, d.sq_n, sh.H(), sh.W(), lane, m0);
   } else if (cur < n_comp) {
     CompRec r = e.comps[cur];
-    footprint_mask<RPL, T>(occ, r.h, r.w, d.H, d.W, lane, m0);
-    footprint_mask<RPL, T>(occ, r.w, r.h, d.H, d.W, lane, m1);
+    footprint_mask<RPL, T>(occ, r.h, r.w, sh.H(), sh.W(), lane, m0);
+    if (r.h == r.w) {
+#pragma unroll
+      for (int k = 0; k < RPL; ++k) m1[k] = m0[k];
+    } else {
+      footprint_mask<RPL, T>(occ, r.w, r.h, sh.H(), sh.W(), lane, m1);
+    }
   }
   T any = T(0);
 #pragma unroll
@@ -342,21 +549,18 @@ __device__ __forceinline__ bool next_masks(const Dims& d, const Env<T>& e, const
 }
 
 // reset(): bank record -> state, empty board (rect:310-351, pin:1544-1597).
-template <int RPL, typename T>
-__device__ __forceinline__ void load_instance(const Params& p, Env<T>& e, uint32_t slot,
-                                              uint64_t episode_no, int lane) {
-  const Dims& d = p.d;
-  if (d.kind != 0) {
-    const uint8_t* rec = p.bank + (size_t)slot * d.rec_stride;
+template <int RPL, typename T, typename S>
+__device__ __forceinline__ void load_instance(const S& sh, const Params& p, Env<T>& e,
+                                              uint32_t slot, uint64_t episode_no, int lane) {
+  if (sh.kind() != 0) {
+    const uint8_t* rec = p.bank + (size_t)slot * sh.rec_stride();
     // header (16 B) then comps/pins; state has the 16-byte EnvDyn in between
     if (lane == 0) *reinterpret_cast<uint4*>(e.sm) = *reinterpret_cast<const uint4*>(rec);
-    const uint4* s = reinterpret_cast<const uint4*>(rec + 16);
-    uint4* dd = reinterpret_cast<uint4*>(e.sm + 32);
-    for (int i = lane; i < ((d.rec_stride - 16) >> 4); i += 32) dd[i] = s[i];
+    copy16(e.sm + 32, rec + 16, sh.rec_stride() - 16, lane);
   }
   __syncwarp();
   if (lane == 0) {
-    if (d.kind == 0) { e.hdr->n_comp = 1; e.hdr->n_nets = 0; e.hdr->n_pins = 0; e.hdr->pad = 0; }
+    if (sh.kind() == 0) { e.hdr->n_comp = 1; e.hdr->n_nets = 0; e.hdr->n_pins = 0; e.hdr->pad = 0; }
     e.hdr->cur = 0;
     e.hdr->flags = 0;
     e.hdr->slot = slot;
@@ -367,129 +571,6 @@ __device__ __forceinline__ void load_instance(const Params& p, Env<T>& e, uint32
 #pragma unroll
   for (int k = 0; k < RPL; ++k) e.occ[lane + 32 * k] = T(0);
   __syncwarp();
-}
-
-// ---------------------------------------------------------------------------
-// K3 (K1/K2): step
-// ---------------------------------------------------------------------------
-template <int RPL, typename T>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const Params p) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  const Dims& d = p.d;
-  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
-  const int env = blockIdx.x * kWarpsPerCta + wic;
-  if (env >= p.n_envs) return;
-  Env<T> e(smem + (size_t)wic * d.sm_stride, d, 32 * RPL);
-  uint8_t* gstate = p.state + (size_t)env * d.st_stride;
-  load_state(e.sm, gstate, d.st_stride, lane);
-  __syncwarp();
-
-  T occ[RPL];
-#pragma unroll
-  for (int k = 0; k < RPL; ++k) occ[k] = e.occ[lane + 32 * k];
-
-  // decode the action (FlatteningActionWrapper*: env_wrappers.py:80-98, wrapper_square.py:54-69)
-  int o = 0, x, y;
-  if (p.action_format == 1) {
-    int a = p.actions[env];
-    int hw = d.H * d.W;
-    if (a < 0) { o = -1; x = y = 0; }
-    else { o = a / hw; int rem = a - o * hw; x = rem / d.W; y = rem - x * d.W; }
-  } else if (d.kind == 0) {
-    x = p.actions[2 * env]; y = p.actions[2 * env + 1];
-  } else {
-    o = p.actions[3 * env]; x = p.actions[3 * env + 1]; y = p.actions[3 * env + 2];
-  }
-
-  const int n_comp = e.hdr->n_comp;
-  int cur = e.hdr->cur;
-  int ph = d.sq_n, pw = d.sq_n, ch = 0, cw = 0;
-  bool in_range = (unsigned)o < (unsigned)d.O && (unsigned)x < (unsigned)d.H &&
-                  (unsigned)y < (unsigned)d.W;
-  if (d.kind != 0) {
-    in_range = in_range && cur < n_comp;
-    if (in_range) {
-      CompRec r = e.comps[cur];
-      ch = r.h; cw = r.w;
-      ph = (o & 1) ? cw : ch;  // footprint (h,w) for o in {0,2}, (w,h) for {1,3}: pin:1755-1760
-      pw = (o & 1) ? ch : cw;
-    }
-  }
-  // validate_action == mask lookup (pin:1712-1736); the mask bit is recomputed here.
-  bool valid = in_range && x + ph <= d.H && y + pw <= d.W;
-  T cols = T(0);
-  if (valid) {
-    cols = low_mask<T>(pw) << y;
-    bool clash = false;
-#pragma unroll
-    for (int k = 0; k < RPL; ++k) {
-      int row = lane + 32 * k;
-      if (row >= x && row < x + ph && (occ[k] & cols)) clash = true;
-    }
-    valid = !__any_sync(kFull, clash);
-  }
-
-  if (valid) {
-#pragma unroll
-    for (int k = 0; k < RPL; ++k) {  // update_grid (pin:1738-1765)
-      int row = lane + 32 * k;
-      if (row >= x && row < x + ph) occ[k] |= cols;
-      e.occ[row] = occ[k];
-    }
-    if (d.kind != 0) {
-      if (lane == 0) { e.comps[cur].x = (uint8_t)x; e.comps[cur].y = (uint8_t)y; }
-      if (d.kind >= 2 && o != 0) {  // Component.place_component (pin:156-204): rotate in place
-        const int n_pins = e.hdr->n_pins;
-        for (int q = lane; q < n_pins; q += 32) {
-          PinRec pr = e.pins[q];
-          if (pr.comp != cur) continue;
-          int rx = pr.rx, ry = pr.ry, nx, ny;
-          if (o == 1) { nx = ry; ny = ch - rx - 1; }
-          else if (o == 2) { nx = ch - rx - 1; ny = cw - ry - 1; }
-          else { nx = cw - ry - 1; ny = rx; }
-          e.pins[q].rx = (uint8_t)nx;
-          e.pins[q].ry = (uint8_t)ny;
-        }
-      }
-      cur += 1;
-    }
-  }
-  __syncwarp();
-
-  T m0[RPL], m1[RPL];
-  bool any = next_masks<RPL, T>(d, e, occ, cur, n_comp, lane, m0, m1);
-  const bool all_placed = d.kind != 0 && cur == n_comp;
-  const bool done = valid ? !any : true;  // compute_if_done (pin:1872-1886); invalid -> done
-  const bool route = d.kind >= 2 && done && all_placed;  // find_reward needs the routes
-  double reward;
-  if (d.kind <= 1) reward = valid ? 1.0 : 0.0;      // square:115-153, rect:405-432
-  else reward = done ? d.pen_reward : 0.0;          // pin:1669-1677, 899-909
-
-  if (lane == 0) {
-    e.hdr->cur = (uint8_t)cur;
-    e.hdr->ep_len += 1;
-    if (!route) e.dyn->ep_return += reward;
-  }
-  __syncwarp();
-  // write the state back (only the parts a step can change)
-  {
-    uint4* g4 = reinterpret_cast<uint4*>(gstate);
-    const uint4* s4 = reinterpret_cast<const uint4*>(e.sm);
-    if (lane < 2) g4[lane] = s4[lane];
-    if (valid) {
-      for (int i = 2 + lane; i < (d.st_stride >> 4); i += 32) g4[i] = s4[i];
-    }
-  }
-
-  if (!(done && d.autoreset)) write_obs<RPL, T>(p, e, env, lane, m0, m1);
-
-  if (lane == 0) {
-    p.out.done[env] = done ? 1 : 0;
-    if (!route) {
-      p.out.reward[env] = reward;
-      if (d.kind >= 2 && done) { p.out.wl[env] = d.pen_wl; p.out.ni[env] = d.pen_ni; }
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------
@@ -517,80 +598,150 @@ __device__ __forceinline__ bool segments_cross(double x1, double y1, double x2, 
          fmin(y1, y2) <= py && py <= fmax(y1, y2) && fmin(y3, y4) <= py && py <= fmax(y3, y4);
 }
 
+// Per-warp scratch of the reward.  A route is stored per pin: the segment "headed" by
+// pin q runs from (px[q], py[q]) to (x2[q], y2[q]); box[q] is a conservative integer
+// bounding box (x0 | y0<<8 | x1<<16 | y1<<24), kNoBox when pin q heads no segment.
+constexpr uint32_t kNoBox = 0x0000ffffu;
 struct RouteScratch {
-  int16_t* px;       // [max_pins] absolute x of pin q
-  int16_t* py;
-  uint16_t* nxt;     // [max_pins] beam route: next pin on the path, 0xFFFF = path end
-  uint16_t* start;   // [max_nets] beam route: first pin of the path of each net
-  uint16_t* net_off; // [max_nets + 1]
-  double* cx;        // [max_nets] centroid
+  double* x2;
+  double* y2;
+  double* dist;
+  double* cx;         // [K] centroid per net
   double* cy;
-  double* dist;      // [max_pins] segment length of the segment headed by pin q
+  uint32_t* box;
+  uint32_t* queue;    // [kPairQueue] candidate pairs (s << 16 | t)
+  int16_t* px;
+  int16_t* py;
+  uint16_t* nxt;      // beam route: next pin on the path, 0xFFFF = path end
+  uint16_t* net_off;  // [K + 1] first pin of each net (pins are net-major)
+  uint16_t* start;    // [K] beam route: first pin of the path
 };
 
-__device__ __forceinline__ RouteScratch route_scratch(uint8_t* scr, const Dims& d) {
+__device__ __forceinline__ RouteScratch route_scratch(uint8_t* scr, int max_pins, int K) {
   RouteScratch r;
-  const int nets = d.K;  // K = max_num_nets + 1 >= n_nets + 1
   uint8_t* q = scr;
-  r.cx = reinterpret_cast<double*>(q); q += nets * 8;
-  r.cy = reinterpret_cast<double*>(q); q += nets * 8;
-  r.dist = reinterpret_cast<double*>(q); q += d.max_pins * 8;
-  r.px = reinterpret_cast<int16_t*>(q); q += d.max_pins * 2;
-  r.py = reinterpret_cast<int16_t*>(q); q += d.max_pins * 2;
-  r.net_off = reinterpret_cast<uint16_t*>(q); q += (nets + 1) * 2;
-  r.start = reinterpret_cast<uint16_t*>(q); q += nets * 2;
-  r.nxt = reinterpret_cast<uint16_t*>(q);
+  r.x2 = reinterpret_cast<double*>(q); q += max_pins * 8;
+  r.y2 = reinterpret_cast<double*>(q); q += max_pins * 8;
+  r.dist = reinterpret_cast<double*>(q); q += max_pins * 8;
+  r.cx = reinterpret_cast<double*>(q); q += K * 8;
+  r.cy = reinterpret_cast<double*>(q); q += K * 8;
+  r.box = reinterpret_cast<uint32_t*>(q); q += max_pins * 4;
+  r.queue = reinterpret_cast<uint32_t*>(q); q += kPairQueue * 4;
+  r.px = reinterpret_cast<int16_t*>(q); q += max_pins * 2;
+  r.py = reinterpret_cast<int16_t*>(q); q += max_pins * 2;
+  r.nxt = reinterpret_cast<uint16_t*>(q); q += max_pins * 2;
+  r.net_off = reinterpret_cast<uint16_t*>(q); q += (K + 1) * 2;
+  r.start = reinterpret_cast<uint16_t*>(q);
   return r;
 }
 
-__host__ __device__ inline int route_scratch_bytes(int max_pins, int K) {
-  return K * 16 + max_pins * 8 + max_pins * 4 + (K + 1) * 2 + K * 2 + max_pins * 2 + 16;
+__device__ __forceinline__ uint32_t make_box(double xa, double ya, double xb, double yb) {
+  int x0 = (int)floor(fmin(xa, xb)), x1 = (int)ceil(fmax(xa, xb));
+  int y0 = (int)floor(fmin(ya, yb)), y1 = (int)ceil(fmax(ya, yb));
+  return (uint32_t)x0 | ((uint32_t)y0 << 8) | ((uint32_t)x1 << 16) | ((uint32_t)y1 << 24);
 }
 
-// Centroid route (route_pins_centroid, pin:1296-1324): crossings + wirelength.
-// Segment "headed" by pin q: (pin q, centroid of its net); for 2-pin nets the
-// only segment is (pin 0, pin 1).
+__device__ __forceinline__ bool boxes_touch(uint32_t a, uint32_t b) {
+  uint32_t lo = __vmaxu4(a, b) & 0xffffu;  // max of the two lower corners (bytes 0,1)
+  uint32_t hi = __vminu4(a, b) >> 16;      // min of the two upper corners
+  return __vcmpleu4(lo, hi) == 0xffffffffu;
+}
+
+// positions, net ranges, centroids (get_net_pin_positions pin:1266-1280, get_centroid :1282-1294)
+template <typename T>
+__device__ __forceinline__ void route_prepare(const Env<T>& e, const RouteScratch& rs, int lane,
+                                              int n_pins, int n_nets) {
+  for (int q = lane; q < n_pins; q += 32) {
+    PinRec pr = e.pins[q];
+    CompRec r = e.comps[pr.comp];
+    rs.px[q] = (int16_t)(r.x + pr.rx);
+    rs.py[q] = (int16_t)(r.y + pr.ry);
+    if (q == 0 || e.pins[q - 1].net != pr.net) rs.net_off[pr.net] = (uint16_t)q;
+  }
+  if (lane == 0) rs.net_off[n_nets] = (uint16_t)n_pins;
+  __syncwarp();
+  // exact integer sums, one correctly rounded division per coordinate
+  for (int net = lane; net < n_nets; net += 32) {
+    int lo = rs.net_off[net], hi = rs.net_off[net + 1], sx = 0, sy = 0;
+    for (int q = lo; q < hi; ++q) { sx += rs.px[q]; sy += rs.py[q]; }
+    rs.cx[net] = (double)sx / (double)(hi - lo);
+    rs.cy[net] = (double)sy / (double)(hi - lo);
+  }
+  __syncwarp();
+}
+
+// find_num_intersection (pin:663-685) over the per-pin segment arrays.  Lane t owns
+// segment t and walks the segments s of earlier nets; pairs whose integer boxes do
+// not touch cannot intersect (the reference requires the point inside both boxes),
+// the others are queued and tested 32 at a time with the reference's float64 formula.
+template <typename T>
+__device__ __forceinline__ int count_crossings(const Env<T>& e, const RouteScratch& rs, int lane,
+                                               int n_pins) {
+  int cnt = 0, qn = 0;
+  auto heavy = [&](uint32_t pr) -> int {
+    int s = pr >> 16, t = pr & 0xffffu;
+    return segments_cross((double)rs.px[s], (double)rs.py[s], rs.x2[s], rs.y2[s],
+                          (double)rs.px[t], (double)rs.py[t], rs.x2[t], rs.y2[t]) ? 1 : 0;
+  };
+  for (int t0 = 0; t0 < n_pins; t0 += 32) {
+    const int t = t0 + lane;
+    uint32_t mine = kNoBox;
+    int my_hi = 0;
+    if (t < n_pins) {
+      mine = rs.box[t];
+      if (mine != kNoBox) my_hi = rs.net_off[e.pins[t].net];  // segments of earlier nets only
+    }
+    const int smax = __reduce_max_sync(kFull, my_hi);
+    for (int s = 0; s < smax; ++s) {
+      const uint32_t other = rs.box[s];
+      if (other == kNoBox) continue;  // warp-uniform
+      const bool pass = s < my_hi && boxes_touch(mine, other);
+      const unsigned b = __ballot_sync(kFull, pass);
+      if (b == 0) continue;
+      if (pass) rs.queue[qn + __popc(b & ((1u << lane) - 1u))] = ((uint32_t)s << 16) | (uint32_t)t;
+      qn += __popc(b);
+      __syncwarp();
+      if (qn >= 32) {
+        qn -= 32;
+        cnt += heavy(rs.queue[qn + lane]);
+        __syncwarp();
+      }
+    }
+  }
+  if (lane < qn) cnt += heavy(rs.queue[lane]);
+  __syncwarp();
+  return __reduce_add_sync(kFull, cnt);
+}
+
+// Centroid route (route_pins_centroid, pin:1296-1324): segment headed by pin q =
+// (pin q, centroid of its net); a 2-pin net has the single segment (pin 0, pin 1).
 template <typename T>
 __device__ __forceinline__ void centroid_route(const Dims& d, const Env<T>& e,
                                                const RouteScratch& rs, int lane, int n_pins,
-                                               int n_nets, int& crossings, double& wl) {
-  auto head = [&](int q, double& x2, double& y2) -> bool {
-    int net = e.pins[q].net;
-    int lo = rs.net_off[net], cnt = rs.net_off[net + 1] - lo;
-    if (cnt == 2) {
-      if (q != lo) return false;
-      x2 = (double)rs.px[q + 1]; y2 = (double)rs.py[q + 1];
-    } else {
-      x2 = rs.cx[net]; y2 = rs.cy[net];
-    }
-    return true;
-  };
-  int cnt = 0;
-  for (int s = 0; s < n_pins; ++s) {
-    double sx2, sy2;
-    if (!head(s, sx2, sy2)) continue;  // warp-uniform
-    const double sx1 = (double)rs.px[s], sy1 = (double)rs.py[s];
-    const int snet = e.pins[s].net;
-    // segments of later nets start at the first pin of net snet+1
-    for (int t = rs.net_off[snet + 1] + lane; t < n_pins; t += 32) {
-      double tx2, ty2;
-      if (!head(t, tx2, ty2)) continue;
-      if (segments_cross(sx1, sy1, sx2, sy2, (double)rs.px[t], (double)rs.py[t], tx2, ty2)) ++cnt;
-    }
-  }
-  for (int off = 16; off; off >>= 1) cnt += __shfl_xor_sync(kFull, cnt, off);
-  crossings = cnt;
-  // find_wirelength (pin:741-759): lengths in parallel, then the reference's sequential sum
+                                               int& crossings, double& wl) {
   for (int q = lane; q < n_pins; q += 32) {
-    double x2, y2, v = -1.0;
-    if (head(q, x2, y2)) v = norm2((double)rs.px[q] - x2, (double)rs.py[q] - y2, d.norm_fma);
-    rs.dist[q] = v;
+    const int net = e.pins[q].net;
+    const int lo = rs.net_off[net], cnt = rs.net_off[net + 1] - lo;
+    double x2 = 0.0, y2 = 0.0, len = -1.0;
+    uint32_t box = kNoBox;
+    if (cnt != 2 || q == lo) {
+      if (cnt == 2) { x2 = (double)rs.px[q + 1]; y2 = (double)rs.py[q + 1]; }
+      else { x2 = rs.cx[net]; y2 = rs.cy[net]; }
+      const double x1 = (double)rs.px[q], y1 = (double)rs.py[q];
+      box = make_box(x1, y1, x2, y2);
+      len = norm2(x1 - x2, y1 - y2, d.norm_fma);
+    }
+    rs.x2[q] = x2; rs.y2[q] = y2; rs.box[q] = box; rs.dist[q] = len;
   }
   __syncwarp();
+  crossings = count_crossings<T>(e, rs, lane, n_pins);
+  // find_wirelength (pin:741-759): the reference's sequential float64 sum, net by net
   double acc = 0.0;
   if (lane == 0)
-    for (int q = 0; q < n_pins; ++q)
-      if (rs.dist[q] >= 0.0) acc += rs.dist[q];
+    for (int q = 0; q < n_pins; ++q) {
+      double v = rs.dist[q];
+      if (v >= 0.0) acc += v;
+    }
   wl = __shfl_sync(kFull, acc, 0);
   __syncwarp();
 }
@@ -601,58 +752,30 @@ __device__ __forceinline__ void centroid_route(const Dims& d, const Env<T>& e,
 
 namespace pcb {
 
-// ---------------------------------------------------------------------------
-// K4 + K6: terminal kernel.  Runs after step_kernel; a warp whose environment did
-// not finish exits at once.  For a finished environment: the routing reward when
-// every component is placed (pin kinds), episode statistics, and -- with
-// auto-reset -- the next instance from the bank plus its first observation.
-// ---------------------------------------------------------------------------
-template <int RPL, typename T>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) terminal_kernel(const Params p) {
-  extern __shared__ __align__(16) uint8_t smem[];
+// End of an episode: routing reward when everything is placed (pin kinds), episode
+// statistics, and with auto-reset the next instance + its first observation.
+// BEAM = false compiles the beam router out (the fused path of step_kernel).
+template <int RPL, typename T, typename S, bool BEAM>
+__device__ __forceinline__ void finish_episode(const S& sh, const Params& p, Env<T>& e, int env,
+                                               int lane, double reward_in, uint8_t* gstate) {
   const Dims& d = p.d;
-  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
-  const int env = blockIdx.x * kWarpsPerCta + wic;
-  if (env >= p.n_envs) return;
-  if (!p.out.done[env]) return;
-  Env<T> e(smem + (size_t)wic * d.sm_stride, d, 32 * RPL);
-  uint8_t* gstate = p.state + (size_t)env * d.st_stride;
-  load_state(e.sm, gstate, d.st_stride, lane);
-  __syncwarp();
-
+  const int kind = sh.kind();
   const int n_comp = e.hdr->n_comp, n_pins = e.hdr->n_pins, n_nets = e.hdr->n_nets;
-  double reward, wl = 0.0, ni = 0.0;
-  const bool route = d.kind >= 2 && e.hdr->cur == n_comp;
+  double reward = reward_in, wl = 0.0, ni = 0.0;
+  const bool route = kind >= 2 && e.hdr->cur == n_comp;
   if (route) {
-    RouteScratch rs = route_scratch(e.scr, d);
-    // get_net_pin_positions (pin:1266-1280): pins are net-major, so a net is a range
-    for (int q = lane; q < n_pins; q += 32) {
-      PinRec pr = e.pins[q];
-      CompRec r = e.comps[pr.comp];
-      rs.px[q] = (int16_t)(r.x + pr.rx);
-      rs.py[q] = (int16_t)(r.y + pr.ry);
-      if (q == 0 || e.pins[q - 1].net != pr.net) rs.net_off[pr.net] = (uint16_t)q;
-    }
-    if (lane == 0) rs.net_off[n_nets] = (uint16_t)n_pins;
-    __syncwarp();
-    // get_centroid (pin:1282-1294): exact integer sums, one division per coordinate
-    for (int net = lane; net < n_nets; net += 32) {
-      int lo = rs.net_off[net], hi = rs.net_off[net + 1], sx = 0, sy = 0;
-      for (int q = lo; q < hi; ++q) { sx += rs.px[q]; sy += rs.py[q]; }
-      rs.cx[net] = (double)sx / (double)(hi - lo);
-      rs.cy[net] = (double)sy / (double)(hi - lo);
-    }
-    __syncwarp();
+    RouteScratch rs = route_scratch(e.scr, sh.max_pins(), sh.K());
+    route_prepare<T>(e, rs, lane, n_pins, n_nets);
     int crossings = 0;
     double length = 0.0;
-    if (d.reward_type == 0) {
-      centroid_route<T>(d, e, rs, lane, n_pins, n_nets, crossings, length);
-    } else {
+    if (!BEAM || d.reward_type == 0) {
+      centroid_route<T>(d, e, rs, lane, n_pins, crossings, length);
+    } else if constexpr (BEAM) {
       beam_paths<T>(d, e, rs, lane, n_nets);
       beam_route<T>(d, e, rs, lane, n_pins, n_nets, crossings, length);
       if (d.reward_type == 2) {  // "both": fewer crossings wins, beam on ties (pin:643-661)
         int c2; double l2;
-        centroid_route<T>(d, e, rs, lane, n_pins, n_nets, c2, l2);
+        centroid_route<T>(d, e, rs, lane, n_pins, c2, l2);
         if (c2 < crossings) { crossings = c2; length = l2; }
       }
     }
@@ -660,9 +783,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) terminal_kernel(const Param
     ni = (double)crossings / d.ni_norm; // pin:922-924
     reward = -1.0 * (d.ww * wl + d.wi * ni);
     if (lane == 0) { p.out.reward[env] = reward; p.out.wl[env] = wl; p.out.ni[env] = ni; }
-  } else {
-    reward = p.out.reward[env];
-    if (d.kind >= 2) { wl = d.pen_wl; ni = d.pen_ni; }
+  } else if (kind >= 2) {
+    wl = d.pen_wl; ni = d.pen_ni;
   }
 
   const bool first_report = !(e.hdr->flags & kFlagFinished);
@@ -675,7 +797,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) terminal_kernel(const Param
       atomicAdd(st + 0, 1.0);
       atomicAdd(st + 1, ret);
       atomicAdd(st + 2, (double)e.hdr->ep_len);
-      if (d.kind >= 2) { atomicAdd(st + 3, wl); atomicAdd(st + 4, ni); }
+      if (kind >= 2) { atomicAdd(st + 3, wl); atomicAdd(st + 4, ni); }
     }
   }
   __syncwarp();
@@ -692,26 +814,175 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) terminal_kernel(const Param
   if (p.bank_count) slot %= p.bank_count;
   uint64_t epno = e.dyn->episode_no + 1;
   __syncwarp();
-  load_instance<RPL, T>(p, e, slot, epno, lane);
+  load_instance<RPL, T, S>(sh, p, e, slot, epno, lane);
   T occ[RPL], m0[RPL], m1[RPL];
 #pragma unroll
   for (int k = 0; k < RPL; ++k) occ[k] = T(0);
-  next_masks<RPL, T>(d, e, occ, 0, e.hdr->n_comp, lane, m0, m1);
-  copy_out(gstate, e.sm, d.st_stride, lane);
-  write_obs<RPL, T>(p, e, env, lane, m0, m1);
+  next_masks<RPL, T, S>(sh, d, e, occ, 0, e.hdr->n_comp, lane, m0, m1);
+  copy16(gstate, e.sm, sh.st_stride(), lane);
+  write_obs<RPL, T, S>(sh, p, e, env, lane, occ, m0, m1);
+  if (p.actions_out)
+    sample_action<RPL, T, S>(sh, m0, m1, p.seed, env, p.step_no + 1, lane, p.actions_out);
+}
+
+// ---------------------------------------------------------------------------
+// K1/K2/K3 (+ fused K4/K6/K7): step
+// ---------------------------------------------------------------------------
+template <int RPL, typename T, typename S>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const Params p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const Dims& d = p.d;
+  const S sh(d);
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  const int env = blockIdx.x * kWarpsPerCta + wic;
+  if (env >= p.n_envs) return;
+  Env<T> e(smem + (size_t)wic * sh.sm_stride(), sh);
+  uint8_t* gstate = p.state + (size_t)env * sh.st_stride();
+  copy16(e.sm, gstate, sh.st_stride(), lane);
+
+  // decode the action (FlatteningActionWrapper*: env_wrappers.py:80-98, wrapper_square.py:54-69)
+  const int kind = sh.kind();
+  int o = 0, x, y;
+  if (p.action_format == 1) {
+    int a = p.actions[env];
+    int hw = sh.H() * sh.W();
+    if (a < 0) { o = -1; x = y = 0; }
+    else { o = a / hw; int rem = a - o * hw; x = rem / sh.W(); y = rem - x * sh.W(); }
+  } else if (kind == 0) {
+    x = p.actions[2 * env]; y = p.actions[2 * env + 1];
+  } else {
+    o = p.actions[3 * env]; x = p.actions[3 * env + 1]; y = p.actions[3 * env + 2];
+  }
+  __syncwarp();
+
+  T occ[RPL];
+#pragma unroll
+  for (int k = 0; k < RPL; ++k) occ[k] = e.occ[lane + 32 * k];
+  const int n_comp = e.hdr->n_comp;
+  int cur = e.hdr->cur;
+  int ph = d.sq_n, pw = d.sq_n, ch = 0, cw = 0;
+  bool in_range = (unsigned)o < (unsigned)sh.O() && (unsigned)x < (unsigned)sh.H() &&
+                  (unsigned)y < (unsigned)sh.W();
+  if (kind != 0) {
+    in_range = in_range && cur < n_comp;
+    if (in_range) {
+      CompRec r = e.comps[cur];
+      ch = r.h; cw = r.w;
+      ph = (o & 1) ? cw : ch;  // footprint (h,w) for o in {0,2}, (w,h) for {1,3}: pin:1755-1760
+      pw = (o & 1) ? ch : cw;
+    }
+  }
+  // validate_action == mask lookup (pin:1712-1736); the mask bit is recomputed here.
+  bool valid = in_range && x + ph <= sh.H() && y + pw <= sh.W();
+  T cols = T(0);
+  if (valid) {
+    cols = low_mask<T>(pw) << y;
+    bool clash = false;
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) {
+      int row = lane + 32 * k;
+      if (row >= x && row < x + ph && (occ[k] & cols)) clash = true;
+    }
+    valid = !__any_sync(kFull, clash);
+  }
+
+  if (valid) {
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) {  // update_grid (pin:1738-1765)
+      int row = lane + 32 * k;
+      if (row >= x && row < x + ph) occ[k] |= cols;
+      e.occ[row] = occ[k];
+    }
+    if (kind != 0) {
+      if (lane == 0) { e.comps[cur].x = (uint8_t)x; e.comps[cur].y = (uint8_t)y; }
+      if (kind >= 2 && o != 0) {  // Component.place_component (pin:156-204): rotate in place
+        const int n_pins = e.hdr->n_pins;
+        for (int q = lane; q < n_pins; q += 32) {
+          PinRec pr = e.pins[q];
+          if (pr.comp != cur) continue;
+          int rx = pr.rx, ry = pr.ry, nx, ny;
+          if (o == 1) { nx = ry; ny = ch - rx - 1; }
+          else if (o == 2) { nx = ch - rx - 1; ny = cw - ry - 1; }
+          else { nx = cw - ry - 1; ny = rx; }
+          e.pins[q].rx = (uint8_t)nx;
+          e.pins[q].ry = (uint8_t)ny;
+        }
+      }
+      cur += 1;
+    }
+  }
+  __syncwarp();
+
+  T m0[RPL], m1[RPL];
+  const bool any = next_masks<RPL, T, S>(sh, d, e, occ, cur, n_comp, lane, m0, m1);
+  const bool all_placed = kind != 0 && cur == n_comp;
+  const bool done = valid ? !any : true;  // compute_if_done (pin:1872-1886); invalid -> done
+  const bool route = kind >= 2 && done && all_placed;  // find_reward needs the routes
+  double reward;
+  if (kind <= 1) reward = valid ? 1.0 : 0.0;      // square:115-153, rect:405-432
+  else reward = done ? d.pen_reward : 0.0;        // pin:1669-1677, 899-909
+
+  if (lane == 0) {
+    e.hdr->cur = (uint8_t)cur;
+    e.hdr->ep_len += 1;
+    if (!route) e.dyn->ep_return += reward;
+  }
+  __syncwarp();
+  const bool restart = done && d.autoreset;
+  if (!(restart && p.fuse_terminal)) {  // a restarting env overwrites its state below
+    uint4* g4 = reinterpret_cast<uint4*>(gstate);
+    const uint4* s4 = reinterpret_cast<const uint4*>(e.sm);
+    if (lane < 2) g4[lane] = s4[lane];
+    if (valid)
+      for (int i = 2 + lane; i < (sh.st_stride() >> 4); i += 32) g4[i] = s4[i];
+  }
+
+  if (!restart) {
+    write_obs<RPL, T, S>(sh, p, e, env, lane, occ, m0, m1);
+    if (p.actions_out)  // a finished, not restarting env has no valid action: reports (0,0,0)
+      sample_action<RPL, T, S>(sh, m0, m1, p.seed, env, p.step_no + 1, lane, p.actions_out);
+  }
+  if (lane == 0) {
+    p.out.done[env] = done ? 1 : 0;
+    if (!route) {
+      p.out.reward[env] = reward;
+      if (kind >= 2 && done) { p.out.wl[env] = d.pen_wl; p.out.ni[env] = d.pen_ni; }
+    }
+  }
+  if (done && p.fuse_terminal)
+    finish_episode<RPL, T, S, false>(sh, p, e, env, lane, reward, gstate);
+}
+
+// K4 + K6 as a separate launch (beam / both reward types): a warp whose environment
+// did not finish exits at once.
+template <int RPL, typename T>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) terminal_kernel(const Params p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const Dims& d = p.d;
+  const DynShape sh(d);
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  const int env = blockIdx.x * kWarpsPerCta + wic;
+  if (env >= p.n_envs) return;
+  if (!p.out.done[env]) return;
+  Env<T> e(smem + (size_t)wic * sh.sm_stride(), sh);
+  uint8_t* gstate = p.state + (size_t)env * sh.st_stride();
+  copy16(e.sm, gstate, sh.st_stride(), lane);
+  __syncwarp();
+  finish_episode<RPL, T, DynShape, true>(sh, p, e, env, lane, p.out.reward[env], gstate);
 }
 
 // K6: reset() -- all envs (reset_mask == nullptr) or the masked ones.
-template <int RPL, typename T>
+template <int RPL, typename T, typename S>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) reset_kernel(const Params p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const Dims& d = p.d;
+  const S sh(d);
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const int env = blockIdx.x * kWarpsPerCta + wic;
   if (env >= p.n_envs) return;
   if (p.reset_mask && !p.reset_mask[env]) return;
-  Env<T> e(smem + (size_t)wic * d.sm_stride, d, 32 * RPL);
-  uint8_t* gstate = p.state + (size_t)env * d.st_stride;
+  Env<T> e(smem + (size_t)wic * sh.sm_stride(), sh);
+  uint8_t* gstate = p.state + (size_t)env * sh.st_stride();
   uint32_t slot = (uint32_t)env;
   uint64_t epno = 0;
   if (!p.reset_first) {
@@ -721,119 +992,43 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) reset_kernel(const Params p
     epno = gd->episode_no + 1;
   }
   if (p.bank_count) slot %= p.bank_count;
-  zero_smem(e.sm, d.st_stride, lane);
+  zero_smem(e.sm, sh.st_stride(), lane);
   __syncwarp();
-  load_instance<RPL, T>(p, e, slot, epno, lane);
+  load_instance<RPL, T, S>(sh, p, e, slot, epno, lane);
   T occ[RPL], m0[RPL], m1[RPL];
 #pragma unroll
   for (int k = 0; k < RPL; ++k) occ[k] = T(0);
-  next_masks<RPL, T>(d, e, occ, 0, e.hdr->n_comp, lane, m0, m1);
-  copy_out(gstate, e.sm, d.st_stride, lane);
-  write_obs<RPL, T>(p, e, env, lane, m0, m1);
+  next_masks<RPL, T, S>(sh, d, e, occ, 0, e.hdr->n_comp, lane, m0, m1);
+  copy16(gstate, e.sm, sh.st_stride(), lane);
+  write_obs<RPL, T, S>(sh, p, e, env, lane, occ, m0, m1);
   if (lane == 0) {
     p.out.done[env] = 0;
     p.out.reward[env] = 0.0;
   }
 }
 
-// ---------------------------------------------------------------------------
-// K7: the random policy of agent/random/random_policy_*.py:11-58 -- uniform over
-// np.argwhere(action_mask == 1), i.e. over the set bits of the mask bitboards in
-// (orientation, row, column) order.  Philox4x32-10 keyed by the seed, counter =
-// (env, step).
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t philox_u32(uint64_t seed, uint32_t c0, uint32_t c1,
-                                               uint32_t c2) {
-  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-  uint32_t x0 = c0, x1 = c1, x2 = c2, x3 = 0x5043422du;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    uint32_t hi0 = __umulhi(0xD2511F53u, x0), lo0 = 0xD2511F53u * x0;
-    uint32_t hi1 = __umulhi(0xCD9E8D57u, x2), lo1 = 0xCD9E8D57u * x2;
-    uint32_t y0 = hi1 ^ x1 ^ k0, y1 = lo1, y2 = hi0 ^ x3 ^ k1, y3 = lo0;
-    x0 = y0; x1 = y1; x2 = y2; x3 = y3;
-    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-  }
-  return x0;
-}
-
+// K7 as a stand-alone launch (pcb_sample_random_actions): masks recomputed from the state.
 template <int RPL, typename T>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) sample_kernel(const Params p) {
   const Dims& d = p.d;
+  const DynShape sh(d);
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const int env = blockIdx.x * kWarpsPerCta + wic;
   if (env >= p.n_envs) return;
-  const uint8_t* gstate = p.state + (size_t)env * d.st_stride;
+  const uint8_t* gstate = p.state + (size_t)env * sh.st_stride();
   const EnvHdr* gh = reinterpret_cast<const EnvHdr*>(gstate);
-  const T* gocc = reinterpret_cast<const T*>(gstate + d.st_occ);
-  T occ[RPL], m[2][RPL];
+  const T* gocc = reinterpret_cast<const T*>(gstate + sh.st_occ());
+  T occ[RPL], m0[RPL], m1[RPL];
 #pragma unroll
-  for (int k = 0; k < RPL; ++k) { occ[k] = gocc[lane + 32 * k]; m[0][k] = T(0); m[1][k] = T(0); }
+  for (int k = 0; k < RPL; ++k) { occ[k] = gocc[lane + 32 * k]; m0[k] = T(0); m1[k] = T(0); }
   if (d.kind == 0) {
-    footprint_mask<RPL, T>(occ, d.sq_n, d.sq_n, d.H, d.W, lane, m[0]);
+    footprint_mask<RPL, T>(occ, d.sq_n, d.sq_n, d.H, d.W, lane, m0);
   } else if (gh->cur < gh->n_comp) {
-    CompRec r = reinterpret_cast<const CompRec*>(gstate + d.st_comps)[gh->cur];
-    footprint_mask<RPL, T>(occ, r.h, r.w, d.H, d.W, lane, m[0]);
-    footprint_mask<RPL, T>(occ, r.w, r.h, d.H, d.W, lane, m[1]);
+    CompRec r = reinterpret_cast<const CompRec*>(gstate + sh.st_comps())[gh->cur];
+    footprint_mask<RPL, T>(occ, r.h, r.w, d.H, d.W, lane, m0);
+    footprint_mask<RPL, T>(occ, r.w, r.h, d.H, d.W, lane, m1);
   }
-  // per-lane counts, warp totals per orientation
-  int cnt[2];
-#pragma unroll
-  for (int oo = 0; oo < 2; ++oo) {
-    int c = 0;
-#pragma unroll
-    for (int k = 0; k < RPL; ++k) c += popc_t<T>(m[oo][k]);
-    cnt[oo] = c;
-  }
-  int tot0 = cnt[0], tot1 = cnt[1];
-  for (int off = 16; off; off >>= 1) {
-    tot0 += __shfl_xor_sync(kFull, tot0, off);
-    tot1 += __shfl_xor_sync(kFull, tot1, off);
-  }
-  const int per_pair = tot0 + tot1;
-  const int total = d.O == 4 ? 2 * per_pair : (d.O == 2 ? per_pair : tot0);
-  int ao = 0, ax = 0, ay = 0;
-  if (total > 0) {
-    uint32_t r = philox_u32(p.seed, (uint32_t)env, (uint32_t)p.step_no, (uint32_t)(p.step_no >> 32));
-    int kth = (int)__umulhi(r, (uint32_t)total);  // uniform in [0, total)
-    int obase = 0;
-    if (kth >= per_pair && d.O == 4) { kth -= per_pair; obase = 2; }
-    int oo = 0;
-    if (kth >= tot0) { kth -= tot0; oo = 1; }
-    // rows are visited in order 0..H-1: slot 0 lanes first, then slot 1
-    int found_row = -1, found_col = 0;
-#pragma unroll
-    for (int k = 0; k < RPL; ++k) {
-      int c = popc_t<T>(oo ? m[1][k] : m[0][k]);
-      int incl = c;
-      for (int off = 1; off < 32; off <<= 1) {
-        int v = __shfl_up_sync(kFull, incl, off);
-        if (lane >= off) incl += v;
-      }
-      int slot_total = __shfl_sync(kFull, incl, 31);
-      int excl = incl - c;
-      bool mine = found_row < 0 && kth >= excl && kth < incl;
-      unsigned who = __ballot_sync(kFull, mine);
-      if (who && found_row < 0) {
-        int src = __ffs(who) - 1;
-        int col = 0;
-        if (mine) {
-          T bits = oo ? m[1][k] : m[0][k];
-          int skip = kth - excl;
-          for (int i = 0; i < skip; ++i) bits &= bits - 1;
-          col = sizeof(T) == 8 ? __ffsll((long long)bits) - 1 : __ffs((int)bits) - 1;
-        }
-        found_col = __shfl_sync(kFull, col, src);
-        found_row = src + 32 * k;
-      }
-      if (found_row < 0) kth -= slot_total;
-    }
-    ao = obase + oo; ax = found_row; ay = found_col;
-  }
-  if (lane == 0) {
-    if (d.kind == 0) { p.actions_out[2 * env] = ax; p.actions_out[2 * env + 1] = ay; }
-    else { p.actions_out[3 * env] = ao; p.actions_out[3 * env + 1] = ax; p.actions_out[3 * env + 2] = ay; }
-  }
+  sample_action<RPL, T, DynShape>(sh, m0, m1, p.seed, env, p.step_no, lane, p.actions_out);
 }
 
 }  // namespace pcb

@@ -16,6 +16,12 @@
 
 #include <stdint.h>
 
+#if defined(__CUDACC__)
+#define PCB_HD __host__ __device__
+#else
+#define PCB_HD
+#endif
+
 namespace pcb {
 
 constexpr int kMaxGrid = 64;        // H, W <= 64
@@ -26,6 +32,7 @@ constexpr int kMaxBeamPoints = 15;  // pins per net - 1 when the beam route is u
 constexpr int kMaxBeamWidth = 4;
 constexpr int kWarpsPerCta = 4;
 constexpr int kStatSlots = 32;      // spread of the episode-statistics atomics
+constexpr int kPairQueue = 64;      // candidate segment pairs buffered per warp
 
 enum : uint8_t { kFlagFinished = 1 };
 enum : uint8_t { kPinWinner = 1 };  // last writer of its (component, pin_id) feature row
@@ -57,18 +64,62 @@ struct __align__(8) PinRec {
   uint8_t rank;  // index among the pins of its component, env.pins order
 };
 
+// Byte offsets / element counts derived from the configuration.  constexpr so that
+// the shape-specialised kernels fold them at compile time and the host computes the
+// very same numbers.
+struct Layout {
+  int O, P, F;
+  int st_comps, st_pins, st_occ, st_stride;
+  int rec_comps, rec_pins, rec_stride;
+  int grid_b, mask_b, feat_n, pnum_n, pcat_n, pgrid_b, cgrid_b;
+  int sm_mrow, sm_stage, sm_scr, sm_stride;
+};
+
+PCB_HD constexpr int align16c(int v) { return (v + 15) & ~15; }
+PCB_HD constexpr int maxc(int a, int b) { return a > b ? a : b; }
+
+// terminal-reward scratch per warp: per-pin arrays + per-net arrays + pair queue
+PCB_HD constexpr int route_scratch_bytes(int max_pins, int K) {
+  return max_pins * (8 + 8 + 8 + 4 + 2 + 2 + 2) + K * (8 + 8 + 2 + 2) + 2 + kPairQueue * 4 + 64;
+}
+
+PCB_HD constexpr Layout make_layout(int kind, int H, int W, int C, int mh, int mw, int K,
+                                    int max_pins) {
+  Layout L{};
+  const bool wide = H > 32 || W > 32;
+  const int word = wide ? 8 : 4, rows = wide ? 64 : 32;
+  L.O = kind == 0 ? 1 : (kind == 1 ? 2 : 4);
+  L.P = mh * mw;
+  L.F = kind == 3 ? 5 + L.P : 5;
+  L.st_comps = 32;
+  L.st_pins = L.st_comps + align16c(C * 4);
+  L.st_occ = L.st_pins + align16c(max_pins * 8);
+  L.st_stride = align16c(L.st_occ + rows * word);
+  L.rec_comps = 16;
+  L.rec_pins = L.rec_comps + align16c(C * 4);
+  L.rec_stride = L.rec_pins + align16c(max_pins * 8);
+  L.grid_b = H * W;
+  L.mask_b = L.O * H * W;
+  L.feat_n = C * L.F;
+  L.pnum_n = kind == 2 ? C * L.P * 4 : (kind == 3 ? (C * L.P + 1) * 4 : 0);
+  L.pcat_n = kind == 2 ? C * L.P : (kind == 3 ? (C * L.P + 1) * 2 : 0);
+  L.pgrid_b = kind == 3 ? H * W * K : 0;
+  L.cgrid_b = kind == 3 ? C * mh * mw * K : 0;
+  int stage = maxc(16, (L.pnum_n + L.pcat_n) * 2);
+  if (kind == 3) stage = maxc(maxc(stage, L.feat_n * 4), maxc(L.pgrid_b, L.cgrid_b));
+  L.sm_mrow = L.st_stride;
+  L.sm_stage = L.sm_mrow + 2 * rows * word;
+  L.sm_scr = L.sm_stage + align16c(stage) + 16;
+  L.sm_stride = align16c(L.sm_scr + (kind >= 2 ? route_scratch_bytes(max_pins, K) : 0));
+  return L;
+}
+
 // Everything a kernel needs to know about the configuration; passed by value.
 struct Dims {
-  int kind, H, W, O, C, P, K, max_pins, F;
+  int kind, H, W, C, K, max_pins;
   int mh, mw, sq_n;
   int reward_type, beam_width, norm_fma, autoreset;
-  // byte offsets inside a state record / bank record
-  int st_stride, st_comps, st_pins, st_occ;
-  int rec_stride, rec_comps, rec_pins;
-  // per-env element counts of each observation key
-  int grid_b, mask_b, feat_n, pnum_n, pcat_n, pgrid_b, cgrid_b;
-  // shared memory per warp (bytes) and offsets inside it
-  int sm_stride, sm_mrow, sm_stage, sm_scr;
+  Layout L;
   double ww, wi, wl_norm, ni_norm, pen_reward, pen_wl, pen_ni;
 };
 
@@ -96,16 +147,18 @@ struct Params {
   Out out;
   uint8_t* state;
   const uint8_t* bank;
+  const float* ratio_lut;  // [mh*mw + 1]: float(area / (H*W)), host-evaluated in float64
   uint32_t bank_count;
   int n_envs;
   const int32_t* actions;
   int action_format;
   const uint8_t* reset_mask;
   int reset_first;
-  double* stats;  // [kStatSlots][8]
+  int fuse_terminal;  // 1: step_kernel finishes episodes itself (no beam route needed)
+  double* stats;      // [kStatSlots][8]
   uint64_t seed;
   uint64_t step_no;
-  int32_t* actions_out;
+  int32_t* actions_out;  // != nullptr: also sample the next random action of every env
 };
 
 }  // namespace pcb

@@ -141,6 +141,23 @@ class PcbVecEnv:
             self._h, ctypes.c_uint64(seed), ctypes.c_void_p(out.data_ptr()), self._stream()))
         return out
 
+    def rollout_random(self, n_steps, seed=0, actions_log=None):
+        """n_steps of {device random policy; step} from one C call (simulate() of
+        agent/random/*.py).  actions_log: optional int32 [n_steps, N, k] device tensor."""
+        ptr = None if actions_log is None else ctypes.c_void_p(actions_log.data_ptr())
+        _lib.check(self.lib.pcb_rollout_random(self._h, ctypes.c_uint64(seed), int(n_steps), ptr,
+                                               self._stream()))
+
+    def kernel_timing(self, on):
+        _lib.check(self.lib.pcb_enable_kernel_timing(self._h, 1 if on else 0))
+
+    def kernel_times(self):
+        """{kernel: (total ms, launches)} since the last call; needs kernel_timing(True)."""
+        ms = (ctypes.c_double * 4)()
+        n = (ctypes.c_int64 * 4)()
+        _lib.check(self.lib.pcb_kernel_times(self._h, ms, n))
+        return {k: (ms[i], int(n[i])) for i, k in enumerate(("step", "terminal", "reset", "sample"))}
+
     def step_host(self, actions_np, reward_np, done_np):
         """step() through host buffers (pcb_step_host): H2D actions, D2H reward/done."""
         fmt = 1 if actions_np.ndim == 1 else 0
