@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpcbgpu.so")
+LIB_PATH = os.environ.get("PCB_LIB_PATH") or os.path.join(_HERE, "libpcbgpu.so")
 ABI_VERSION = 1
 
 SYMBOLS = (

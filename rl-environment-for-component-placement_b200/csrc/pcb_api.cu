@@ -87,6 +87,8 @@ namespace {
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
   if (bytes > 48 * 1024) CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  // many small CTAs per SM: ask for the largest shared-memory carve-out
+  CU(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   return 0;
 }
 
@@ -248,7 +250,7 @@ int check_config(const pcb_config_t* c) {
   return 0;
 }
 
-void fill_dims(const pcb_config_t& c, Dims& d) {
+void fill_dims(const pcb_config_t& c, bool fast_board, Dims& d) {
   memset(&d, 0, sizeof d);
   d.kind = c.kind; d.H = c.height; d.W = c.width;
   d.sq_n = c.component_n;
@@ -256,7 +258,7 @@ void fill_dims(const pcb_config_t& c, Dims& d) {
   if (c.kind >= 2) { d.K = c.max_num_nets + 1; d.max_pins = c.max_pins; }
   d.reward_type = c.reward_type; d.beam_width = c.reward_beam_width;
   d.norm_fma = c.norm_uses_fma; d.autoreset = c.autoreset;
-  d.L = make_layout(d.kind, d.H, d.W, d.C, d.mh, d.mw, d.K, d.max_pins);
+  d.L = make_layout(d.kind, d.H, d.W, d.C, d.mh, d.mw, d.K, d.max_pins, fast_board);
   d.ww = c.weight_wirelength; d.wi = c.weight_num_intersections;
   d.wl_norm = c.wirelength_norm; d.ni_norm = c.intersections_norm;
   d.pen_reward = c.penalty_reward; d.pen_wl = c.penalty_wirelength; d.pen_ni = c.penalty_intersections;
@@ -373,7 +375,9 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
   e->step_no = 0; e->launches = 0; e->bank = nullptr; e->bank_count = 0; e->timing = false;
   e->ratio_lut = nullptr; e->d_actions = nullptr; e->d_actions2 = nullptr;
   memset(&e->base, 0, sizeof e->base);
-  fill_dims(*cfg, e->d);
+  fill_dims(*cfg, false, e->d);
+  e->shape_id = cfg->reserved0 == 1 ? 0 : pick_shape(e->d);  // reserved0 == 1 forces the generic kernels (tests)
+  if (e->shape_id) fill_dims(*cfg, true, e->d);  // every FixedShape expands boards from registers
   const Dims& d = e->d;
   e->smem_bytes = (size_t)d.L.sm_stride * kWarpsPerCta;
   if (e->smem_bytes > 200 * 1024) {
@@ -382,7 +386,6 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
   }
   auto cleanup = [&](int code) { pcb_destroy(e); return code; };
 #define TRY(x) do { int rc_ = (x); if (rc_) return cleanup(rc_); } while (0)
-  e->shape_id = cfg->reserved0 == 1 ? 0 : pick_shape(e->d);  // reserved0 == 1 forces the generic kernels (tests)
   e->fuse = d.kind < 2 || d.reward_type == PCB_REWARD_CENTROID;
   switch (e->shape_id) {
     case 1: TRY((set_smem_shape<1, uint32_t, ShapeB>(e->smem_bytes))); break;

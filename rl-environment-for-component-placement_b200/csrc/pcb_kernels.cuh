@@ -34,7 +34,8 @@ constexpr unsigned kFull = 0xffffffffu;
 template <int KIND, int HH, int WW, int CC, int MH, int MW, int KK, int MAXPINS>
 struct FixedShape {
   static constexpr bool fixed = true;
-  static constexpr Layout LL = make_layout(KIND, HH, WW, CC, MH, MW, KK, MAXPINS);
+  static constexpr bool fast_board = HH == WW && (HH == 16 || HH == 32 || HH == 64);
+  static constexpr Layout LL = make_layout(KIND, HH, WW, CC, MH, MW, KK, MAXPINS, fast_board);
   __device__ __forceinline__ explicit FixedShape(const Dims&) {}
   __device__ __forceinline__ constexpr int kind() const { return KIND; }
   __device__ __forceinline__ constexpr int H() const { return HH; }
@@ -105,14 +106,24 @@ __device__ __forceinline__ int ffs_t(T v) {  // index of the lowest set bit, v !
 }
 
 // position of the (n+1)-th set bit (n counted from 0); garbage when v has fewer bits
+__device__ __forceinline__ int nth_bit32(uint32_t v, int n) {
+  int pos = 0;
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    int c = __popc(v & ((1u << w) - 1u));
+    if (n >= c) { n -= c; pos += w; v >>= w; }
+  }
+  return pos;
+}
+
 template <typename T>
 __device__ __forceinline__ int nth_bit(T v, int n) {
   if constexpr (sizeof(T) == 8) {
     unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
     int cl = __popc(lo);
-    return n < cl ? (int)__fns(lo, 0, n + 1) : 32 + (int)__fns(hi, 0, n - cl + 1);
+    return n < cl ? nth_bit32(lo, n) : 32 + nth_bit32(hi, n - cl);
   } else {
-    return (int)__fns((unsigned)v, 0, n + 1);
+    return nth_bit32((unsigned)v, n);
   }
 }
 
@@ -214,12 +225,10 @@ template <typename S>
 struct BoardPath {
   static constexpr bool fast = false;
 };
-template <int KIND, int CC, int MH, int MW, int KK, int MP>
-struct BoardPath<FixedShape<KIND, 32, 32, CC, MH, MW, KK, MP>> { static constexpr bool fast = true; };
-template <int KIND, int CC, int MH, int MW, int KK, int MP>
-struct BoardPath<FixedShape<KIND, 64, 64, CC, MH, MW, KK, MP>> { static constexpr bool fast = true; };
-template <int KIND, int CC, int MH, int MW, int KK, int MP>
-struct BoardPath<FixedShape<KIND, 16, 16, CC, MH, MW, KK, MP>> { static constexpr bool fast = true; };
+template <int KIND, int HH, int WW, int CC, int MH, int MW, int KK, int MP>
+struct BoardPath<FixedShape<KIND, HH, WW, CC, MH, MW, KK, MP>> {
+  static constexpr bool fast = FixedShape<KIND, HH, WW, CC, MH, MW, KK, MP>::fast_board;
+};
 
 template <int RPL, typename T, typename S>
 __device__ __forceinline__ void write_board(const S& sh, uint8_t* dst, const T (&regs)[RPL],
@@ -409,22 +418,35 @@ __device__ __forceinline__ void write_obs(const S& sh, const Params& p, Env<T>& 
 
   // all_components_feature: [h, w, x|-1, y|-1, h*w/(H*W)] (+ pin ids, spatial)
   float* feat = p.out.feat + (size_t)env * sh.feat_n();
-  float* fdst = kind == 3 ? reinterpret_cast<float*>(e.stage) : feat;
-  for (int i = lane; i < sh.feat_n(); i += 32) {
-    int c = i / F, f = i - F * c;
-    float v = 0.f;
-    if (c < n_comp) {
-      CompRec r = e.comps[c];
-      if (f == 0) v = (float)r.h;
-      else if (f == 1) v = (float)r.w;
-      else if (f == 2) v = r.x == 0xFF ? -1.f : (float)r.x;
-      else if (f == 3) v = r.y == 0xFF ? -1.f : (float)r.y;
-      else if (f == 4) v = p.ratio_lut[r.h * r.w];
-      else v = -1.f;
+  if (kind != 3) {
+    for (int c = lane; c < C; c += 32) {  // one lane per component row (5 floats)
+      float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f, f4 = 0.f;
+      if (c < n_comp) {
+        CompRec r = e.comps[c];
+        f0 = (float)r.h; f1 = (float)r.w;
+        f2 = r.x == 0xFF ? -1.f : (float)r.x;
+        f3 = r.y == 0xFF ? -1.f : (float)r.y;
+        f4 = p.ratio_lut[r.h * r.w];
+      }
+      float* row = feat + c * 5;
+      row[0] = f0; row[1] = f1; row[2] = f2; row[3] = f3; row[4] = f4;
     }
-    fdst[i] = v;
-  }
-  if (kind == 3) {
+  } else {
+    float* fdst = reinterpret_cast<float*>(e.stage);
+    for (int i = lane; i < sh.feat_n(); i += 32) {
+      int c = i / F, f = i - F * c;
+      float v = 0.f;
+      if (c < n_comp) {
+        CompRec r = e.comps[c];
+        if (f == 0) v = (float)r.h;
+        else if (f == 1) v = (float)r.w;
+        else if (f == 2) v = r.x == 0xFF ? -1.f : (float)r.x;
+        else if (f == 3) v = r.y == 0xFF ? -1.f : (float)r.y;
+        else if (f == 4) v = p.ratio_lut[r.h * r.w];
+        else v = -1.f;
+      }
+      fdst[i] = v;
+    }
     __syncwarp();
     for (int q = lane; q < n_pins; q += 32) {
       PinRec pr = e.pins[q];
@@ -447,11 +469,22 @@ __device__ __forceinline__ void write_obs(const S& sh, const Params& p, Env<T>& 
   }
   if (kind == 1) return;
 
-  // all_pins_num_feature / all_pins_cat_feature (pin:1521-1542, spatial:1469-1485)
+  // all_pins_num_feature / all_pins_cat_feature (pin:1521-1542, spatial:1469-1485):
+  // zero the env's slice with 16-byte stores, then every winning pin writes its row.
+  // __syncwarp() orders the two phases (they may hit the same bytes from different lanes).
   const int pnum_n = sh.pnum_n(), pcat_n = sh.pcat_n();
-  int16_t* snum = reinterpret_cast<int16_t*>(e.stage);
-  int16_t* scat = snum + pnum_n;
-  zero_smem(e.stage, ((pnum_n + pcat_n) * 2 + 15) & ~15, lane);
+  int16_t* gnum = p.out.pnum + (size_t)env * pnum_n;
+  int16_t* gcat = p.out.pcat + (size_t)env * pcat_n;
+  if ((((pnum_n | pcat_n) * 2) & 15) == 0) {
+    uint4* z = reinterpret_cast<uint4*>(gnum);
+    for (int i = lane; i < (pnum_n >> 3); i += 32) z[i] = make_uint4(0, 0, 0, 0);
+    z = reinterpret_cast<uint4*>(gcat);
+    for (int i = lane; i < (pcat_n >> 3); i += 32) z[i] = make_uint4(0, 0, 0, 0);
+  } else {
+    uint32_t* z = reinterpret_cast<uint32_t*>(gnum);  // pnum_n is a multiple of 4 int16
+    for (int i = lane; i < (pnum_n >> 1); i += 32) z[i] = 0u;
+    for (int i = lane; i < pcat_n; i += 32) gcat[i] = 0;
+  }
   __syncwarp();
   for (int q = lane; q < n_pins; q += 32) {
     PinRec pr = e.pins[q];
@@ -463,18 +496,15 @@ __device__ __forceinline__ void write_obs(const S& sh, const Params& p, Env<T>& 
     // one 8-byte store: [rel_x, rel_y, abs_x, abs_y] as int16
     uint2 v = make_uint2((uint32_t)pr.rx | ((uint32_t)pr.ry << 16),
                          ((uint32_t)ax & 0xffffu) | ((uint32_t)ay << 16));
-    *reinterpret_cast<uint2*>(snum + row * 4) = v;
+    *reinterpret_cast<uint2*>(gnum + row * 4) = v;
     if (kind == 3)
-      *reinterpret_cast<uint32_t*>(scat + row * 2) = (uint32_t)pr.net | ((uint32_t)pr.comp << 16);
+      *reinterpret_cast<uint32_t*>(gcat + row * 2) = (uint32_t)pr.net | ((uint32_t)pr.comp << 16);
     else
-      scat[row] = pr.net;
+      gcat[row] = pr.net;
   }
-  if (kind == 3 && lane == 0) { scat[pcat_n - 2] = -1; scat[pcat_n - 1] = -1; }
-  __syncwarp();
-  copy_out(p.out.pnum + (size_t)env * pnum_n, snum, pnum_n * 2, lane);
-  copy_out(p.out.pcat + (size_t)env * pcat_n, scat, pcat_n * 2, lane);
-  __syncwarp();
+  if (kind == 3 && lane == 0) { gcat[pcat_n - 2] = -1; gcat[pcat_n - 1] = -1; }
   if (kind != 3) return;
+  __syncwarp();
 
   // pin_grid (spatial:1663-1675): channel 0 = occupied cell without a pin,
   // channel net+1 = placed pin of that net.
@@ -829,7 +859,7 @@ __device__ __forceinline__ void finish_episode(const S& sh, const Params& p, Env
 // K1/K2/K3 (+ fused K4/K6/K7): step
 // ---------------------------------------------------------------------------
 template <int RPL, typename T, typename S>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) step_kernel(const Params p) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, PCB_MIN_BLOCKS) step_kernel(const Params p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const Dims& d = p.d;
   const S sh(d);

@@ -30,7 +30,13 @@ constexpr int kMaxPins = 512;       // pin table capacity
 constexpr int kMaxNets = 64;
 constexpr int kMaxBeamPoints = 15;  // pins per net - 1 when the beam route is used
 constexpr int kMaxBeamWidth = 4;
-constexpr int kWarpsPerCta = 4;
+#ifndef PCB_WARPS_PER_CTA
+#define PCB_WARPS_PER_CTA 4
+#endif
+#ifndef PCB_MIN_BLOCKS
+#define PCB_MIN_BLOCKS 12   // __launch_bounds__ min CTAs/SM of the step kernel (caps registers)
+#endif
+constexpr int kWarpsPerCta = PCB_WARPS_PER_CTA;
 constexpr int kStatSlots = 32;      // spread of the episode-statistics atomics
 constexpr int kPairQueue = 64;      // candidate segment pairs buffered per warp
 
@@ -83,8 +89,10 @@ PCB_HD constexpr int route_scratch_bytes(int max_pins, int K) {
   return max_pins * (8 + 8 + 8 + 4 + 2 + 2 + 2) + K * (8 + 8 + 2 + 2) + 2 + kPairQueue * 4 + 64;
 }
 
+// fast_board: the kernel expands bitboards straight from registers (FixedShape 16/32/64
+// square grids) and needs no mask rows in shared memory.
 PCB_HD constexpr Layout make_layout(int kind, int H, int W, int C, int mh, int mw, int K,
-                                    int max_pins) {
+                                    int max_pins, bool fast_board) {
   Layout L{};
   const bool wide = H > 32 || W > 32;
   const int word = wide ? 8 : 4, rows = wide ? 64 : 32;
@@ -108,9 +116,11 @@ PCB_HD constexpr Layout make_layout(int kind, int H, int W, int C, int mh, int m
   int stage = maxc(16, (L.pnum_n + L.pcat_n) * 2);
   if (kind == 3) stage = maxc(maxc(stage, L.feat_n * 4), maxc(L.pgrid_b, L.cgrid_b));
   L.sm_mrow = L.st_stride;
-  L.sm_stage = L.sm_mrow + 2 * rows * word;
-  L.sm_scr = L.sm_stage + align16c(stage) + 16;
-  L.sm_stride = align16c(L.sm_scr + (kind >= 2 ? route_scratch_bytes(max_pins, K) : 0));
+  L.sm_stage = L.sm_mrow + (fast_board ? 0 : 2 * rows * word);
+  // the reward scratch and the observation staging area are never live together
+  L.sm_scr = L.sm_stage;
+  L.sm_stride = align16c(L.sm_stage + maxc(align16c(stage) + 16,
+                                           kind >= 2 ? route_scratch_bytes(max_pins, K) : 0));
   return L;
 }
 
