@@ -15,7 +15,8 @@ from .wrappers import (  # noqa: F401
     FlatteningActionMaskObservationWrapper, FlatteningActionWrapper,
     FlatteningActionMaskObservationWrapperRect, FlatteningActionWrapperRect,
     FlatteningActionMaskObservationWrapperSquare, FlatteningActionWrapperSquare)
-from .rollout import RolloutCollector, allreduce_episode_stats  # noqa: F401
+from .rollout import (RolloutCollector, allreduce_episode_stats, allreduce_stats,  # noqa: F401
+                      shard_range)
 from . import _lib  # noqa: F401
 
 __all__ = ["PcbVecEnv", "GymCompatEnv", "create_env", "init_env", "InstanceBank", "EnvSpec",

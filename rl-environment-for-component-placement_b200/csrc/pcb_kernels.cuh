@@ -189,28 +189,56 @@ __device__ __forceinline__ void rows_ahead(const T (&v)[RPL], int dlt, int lane,
 template <int RPL, typename T>
 __device__ __forceinline__ void footprint_mask(const T (&occ)[RPL], int ph, int pw, int H, int W,
                                                int lane, T (&out)[RPL]) {
+  // horizontal: AND of v >> 0 .. v >> (pw-1); zeros shift in above column W-1
 #pragma unroll
   for (int k = 0; k < RPL; ++k) {
     int row = lane + 32 * k;
     T v = row < H ? (T)(~occ[k] & low_mask<T>(W)) : T(0);
-    // AND of v >> 0 .. v >> (pw-1) by doubling; zeros shift in above column W-1
-    int s = 1;
-    while (2 * s <= pw) { v &= v >> s; s <<= 1; }
-    if (s < pw) v &= v >> (pw - s);
+    if (pw <= 4) {  // the usual component sizes: at most two shift/ANDs
+      T a = v & (v >> 1);
+      T r = pw >= 2 ? a : v;
+      if (pw == 3) r = a & (v >> 2);
+      if (pw == 4) r = a & (a >> 2);
+      v = r;
+    } else {
+      int s = 1;
+      while (2 * s <= pw) { v &= v >> s; s <<= 1; }
+      if (s < pw) v &= v >> (pw - s);
+    }
     out[k] = v;
   }
-  int s = 1;
+  // vertical: AND of rows r .. r+ph-1 (rows past the board count as blocked)
   T t[RPL];
-  while (2 * s <= ph) {
-    rows_ahead<RPL, T>(out, s, lane, t);
+  if (ph <= 4) {
+    if (ph >= 2) {
+      T a[RPL];
+      rows_ahead<RPL, T>(out, 1, lane, t);
 #pragma unroll
-    for (int k = 0; k < RPL; ++k) out[k] &= t[k];
-    s <<= 1;
-  }
-  if (s < ph) {
-    rows_ahead<RPL, T>(out, ph - s, lane, t);
+      for (int k = 0; k < RPL; ++k) a[k] = out[k] & t[k];
+      if (ph >= 3) {
+        T src[RPL];
 #pragma unroll
-    for (int k = 0; k < RPL; ++k) out[k] &= t[k];
+        for (int k = 0; k < RPL; ++k) src[k] = ph == 4 ? a[k] : out[k];
+        rows_ahead<RPL, T>(src, 2, lane, t);
+#pragma unroll
+        for (int k = 0; k < RPL; ++k) a[k] &= t[k];
+      }
+#pragma unroll
+      for (int k = 0; k < RPL; ++k) out[k] = a[k];
+    }
+  } else {
+    int s = 1;
+    while (2 * s <= ph) {
+      rows_ahead<RPL, T>(out, s, lane, t);
+#pragma unroll
+      for (int k = 0; k < RPL; ++k) out[k] &= t[k];
+      s <<= 1;
+    }
+    if (s < ph) {
+      rows_ahead<RPL, T>(out, ph - s, lane, t);
+#pragma unroll
+      for (int k = 0; k < RPL; ++k) out[k] &= t[k];
+    }
   }
 }
 
@@ -386,6 +414,17 @@ __device__ __forceinline__ void sample_action(const S& sh, const T (&m0)[RPL], c
   }
 }
 
+// area / (H*W) as float32(float64 quotient).  With H*W a power of two the quotient is
+// exact, so a float multiply gives the same bits; otherwise the host-built table is read.
+template <typename S>
+__device__ __forceinline__ float area_ratio(const S& sh, const Params& p, int area) {
+  const int hw = sh.H() * sh.W();
+  if constexpr (S::fixed) {
+    if ((hw & (hw - 1)) == 0) return (float)area * (1.0f / (float)hw);
+  }
+  return p.ratio_lut[area];
+}
+
 // ---------------------------------------------------------------------------
 // observation write-out (everything the reference copies into the obs dict:
 // rect:410-416, pin:1680-1687, spatial:1633-1644; layout SURVEY.md Appendix C)
@@ -426,7 +465,7 @@ __device__ __forceinline__ void write_obs(const S& sh, const Params& p, Env<T>& 
         f0 = (float)r.h; f1 = (float)r.w;
         f2 = r.x == 0xFF ? -1.f : (float)r.x;
         f3 = r.y == 0xFF ? -1.f : (float)r.y;
-        f4 = p.ratio_lut[r.h * r.w];
+        f4 = area_ratio(sh, p, r.h * r.w);
       }
       float* row = feat + c * 5;
       row[0] = f0; row[1] = f1; row[2] = f2; row[3] = f3; row[4] = f4;
@@ -442,7 +481,7 @@ __device__ __forceinline__ void write_obs(const S& sh, const Params& p, Env<T>& 
         else if (f == 1) v = (float)r.w;
         else if (f == 2) v = r.x == 0xFF ? -1.f : (float)r.x;
         else if (f == 3) v = r.y == 0xFF ? -1.f : (float)r.y;
-        else if (f == 4) v = p.ratio_lut[r.h * r.w];
+        else if (f == 4) v = area_ratio(sh, p, r.h * r.w);
         else v = -1.f;
       }
       fdst[i] = v;

@@ -61,16 +61,28 @@ class RolloutCollector:
                 "dones": self.dones}
 
 
-def allreduce_episode_stats(env, reset=False):
-    """Sum of the per-GPU episode statistics over all ranks (NCCL over NVLink when
-    torch.distributed runs the nccl backend; gloo on CPU in the tests)."""
+def shard_range(total, rank, world):
+    """Environment ids [lo, hi) owned by `rank`: contiguous, sizes differ by at most one
+    (env ids [g*N/G, (g+1)*N/G) on GPU g)."""
+    base, rem = divmod(int(total), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_stats(stats, device=None):
+    """Sum a dict of float statistics over all ranks (NCCL over NVLink with the nccl
+    backend -- then `device` must be the rank's GPU; gloo on CPU in the tests)."""
     import torch.distributed as dist
 
-    st = env.episode_stats(reset=reset)
-    keys = sorted(st)
+    keys = sorted(stats)
     backend = dist.get_backend() if dist.is_initialized() else None
-    dev = env.device if backend == "nccl" else torch.device("cpu")
-    t = torch.tensor([st[k] for k in keys], dtype=torch.float64, device=dev)
+    dev = device if backend == "nccl" else torch.device("cpu")
+    t = torch.tensor([float(stats[k]) for k in keys], dtype=torch.float64, device=dev)
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return {k: float(v) for k, v in zip(keys, t.tolist())}
+
+
+def allreduce_episode_stats(env, reset=False):
+    """C1: the per-rollout reduction of the device-side episode statistics."""
+    return allreduce_stats(env.episode_stats(reset=reset), env.device)

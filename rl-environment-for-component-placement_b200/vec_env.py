@@ -45,11 +45,13 @@ class PcbVecEnv:
     """
 
     def __init__(self, env_config, num_envs, device=0, autoreset=True, obs_ring=1,
-                 instances=None, bank_size=None, seed=0, norm_uses_fma=True):
+                 instances=None, bank_size=None, seed=0, norm_uses_fma=True, force_generic=False):
         if not torch.cuda.is_available():
             raise RuntimeError("pcbgpu needs a CUDA device; there is no CPU fallback")
         self.lib = _lib.load()
         self.spec = make_spec(env_config, autoreset, obs_ring, norm_uses_fma)
+        if force_generic:  # use the runtime-shaped kernels even for a canonical shape (tests)
+            self.spec.c.reserved0 = 1
         self.kind = self.spec.kind
         self.num_envs = int(num_envs)
         self.device = torch.device("cuda", int(device))

@@ -55,7 +55,7 @@ def float_close(a, b):
 
 
 def run_parity(name, seeds, autoreset=False, p_invalid=0.0, episodes=1, extra_steps=1,
-               stats=None):
+               stats=None, **env_kw):
     """Steps len(seeds) GPU envs and len(seeds) oracle envs in lock-step.
     autoreset=True runs `episodes` episodes per env (instances seed + k*N)."""
     import pcbgpu
@@ -67,7 +67,7 @@ def run_parity(name, seeds, autoreset=False, p_invalid=0.0, episodes=1, extra_st
     insts = None
     if not square:
         insts = [draw_instance(cfg, s + k * 100003) for k in range(episodes) for s in seeds]
-    env = pcbgpu.PcbVecEnv(cfg, N, autoreset=autoreset, instances=insts)
+    env = pcbgpu.PcbVecEnv(cfg, N, autoreset=autoreset, instances=insts, **env_kw)
     C = env.spec.max_num_components
     orcs = [make_oracle(cfg) for _ in seeds]
     rngs = [np.random.default_rng(s) for s in seeds]

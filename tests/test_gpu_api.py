@@ -1,0 +1,163 @@
+"""GPU tests of the API surface around the step kernel: the device random policy,
+the fused rollout, host-buffer stepping, flat actions, the generic (runtime-shaped)
+kernels on the canonical shapes, the rollout collector and the episode statistics."""
+import numpy as np
+import pytest
+import torch
+
+from parity import draw_instance, run_parity
+from ref_harness import CONFIGS
+
+pytestmark = pytest.mark.gpu
+
+
+def make(name, n, **kw):
+    import pcbgpu
+
+    return pcbgpu.PcbVecEnv(CONFIGS[name], n, **kw)
+
+
+@pytest.mark.parametrize("name", ["B", "C", "D"])
+def test_generic_kernels_on_canonical_shapes(name):
+    run_parity(name, range(24), extra_steps=2, force_generic=True)
+    run_parity(name, range(24, 40), autoreset=True, episodes=2, p_invalid=0.1, force_generic=True)
+
+
+@pytest.mark.parametrize("name", ["A", "B", "C", "E", "S_pin", "S_rect"])
+def test_sampler_only_returns_valid_actions(name):
+    env = make(name, 256, autoreset=True, seed=5)
+    obs = env.reset()
+    idx = torch.arange(256, device="cuda")
+    for t in range(12):
+        a = env.sample_random_actions(seed=3).long()
+        mask = obs["action_mask"]
+        picked = mask[idx, a[:, 0], a[:, 1]] if a.shape[1] == 2 else mask[idx, a[:, 0], a[:, 1], a[:, 2]]
+        assert bool((picked == 1).all()), (name, t)
+        obs, r, d, _ = env.step(a.int())
+    env.close()
+
+
+def test_sampler_is_uniform_over_valid_actions():
+    cfg = CONFIGS["B"]
+    inst = draw_instance(cfg, 1)
+    n = 32768
+    env = make("B", n, autoreset=False, instances=[inst])  # every env holds the same instance
+    obs = env.reset()
+    a = env.sample_random_actions(seed=11).long()
+    flat = (a[:, 0] * 16 + a[:, 1]) * 16 + a[:, 2]
+    valid = obs["action_mask"][0].reshape(-1).bool()
+    counts = torch.bincount(flat, minlength=2 * 256).double()
+    assert counts[~valid].sum() == 0
+    k = int(valid.sum())
+    exp = n / k
+    chi2 = float((((counts[valid] - exp) ** 2) / exp).sum())
+    assert chi2 < k + 6 * np.sqrt(2 * k), (chi2, k)  # mean k-1, sd sqrt(2k)
+    env.close()
+
+
+@pytest.mark.parametrize("name", ["C", "C_both", "B", "A"])
+def test_fused_rollout_equals_sample_then_step(name):
+    a, b = make(name, 512, seed=2), make(name, 512, seed=2)
+    a.reset(); b.reset()
+    a.rollout_random(25, seed=9)
+    tot = torch.zeros(512, dtype=torch.float64, device="cuda")
+    for t in range(25):
+        act = b.sample_random_actions(seed=9)
+        _, r, d, _ = b.step(act)
+        tot += r
+    torch.cuda.synchronize()
+    sa, sb = a.episode_stats(), b.episode_stats()
+    assert sa == sb and sa["episodes"] > 0
+    assert np.array_equal(a.occupancy(), b.occupancy())
+    for k in a._obs():
+        assert torch.equal(a._obs()[k], b._obs()[k]), k
+    a.close(); b.close()
+
+
+def test_step_host_and_flat_actions_match_device_step():
+    import pcbgpu
+
+    a, b, c = make("C", 300, seed=4), make("C", 300, seed=4), make("C", 300, seed=4)
+    a.reset(); b.reset(); c.reset()
+    rew = np.zeros(300); done = np.zeros(300, np.uint8)
+    for t in range(14):
+        act = a.sample_random_actions(seed=1).clone()
+        _, r, d, _ = a.step(act)
+        torch.cuda.synchronize()
+        b.step_host(act.cpu().numpy(), rew, done)
+        flat = (act[:, 0].long() * 32 + act[:, 1]) * 32 + act[:, 2]
+        assert torch.equal(c.decode_flat_actions(flat), act)
+        _, r3, d3, _ = c.step(flat.int())
+        torch.cuda.synchronize()
+        assert np.array_equal(r.cpu().numpy(), rew) and np.array_equal(d.cpu().numpy(), done)
+        assert torch.equal(r, r3) and torch.equal(d, d3)
+    assert torch.equal(a.action_mask_flat, c.action_mask.reshape(300, -1))
+    for e in (a, b, c):
+        e.close()
+    assert pcbgpu.PcbVecEnv is not None
+
+
+def test_episode_statistics_and_partial_reset():
+    env = make("C", 128, autoreset=True, seed=8)
+    env.reset()
+    n_done, ret = 0, 0.0
+    for t in range(35):
+        _, r, d, info = env.step(env.sample_random_actions(seed=2))
+        torch.cuda.synchronize()
+        n_done += int(d.sum())
+        ret += float(r.sum())
+        if d.any():
+            i = int(torch.nonzero(d)[0])
+            assert int(info["episode_length"][i]) == 10
+    st = env.episode_stats()
+    assert st["episodes"] == n_done == 128 * 3
+    assert np.isclose(st["sum_return"], ret) and st["sum_length"] == 10 * n_done
+    assert st["steps"] == 35 * 128
+    env.close()
+    env = make("B", 8, autoreset=False, seed=1)
+    env.reset()
+    env.rollout_random(3, seed=0)
+    occ = env.occupancy()
+    mask = torch.tensor([1, 0, 0, 1, 0, 0, 0, 0], dtype=torch.uint8)
+    obs = env.reset(mask=mask)
+    occ2 = env.occupancy()
+    assert not occ2[0].any() and not occ2[3].any() and np.array_equal(occ[1], occ2[1])
+    assert int(obs["placement_mask"][0].sum()) == 0 and int(obs["placement_mask"][1].sum()) == 3
+    env.close()
+
+
+def test_rollout_collector_zero_copy_ring():
+    import pcbgpu
+
+    env = make("D", 64, obs_ring=9, seed=3)
+    col = pcbgpu.RolloutCollector(env, horizon=8, seed=5)
+    assert col.zero_copy
+    out = col.collect()
+    assert out["obs"]["pin_grid"].shape == (9, 64, 32, 32, 6)
+    assert out["actions"].shape == (8, 64, 3) and out["rewards"].shape == (8, 64)
+    # the observation stored for step t is the one the action of step t was valid for
+    t = 5
+    a = out["actions"][t].long()
+    m = out["obs"]["action_mask"][t]
+    assert bool((m[torch.arange(64), a[:, 0], a[:, 1], a[:, 2]] == 1).all())
+    env.close()
+    env = make("B", 32, obs_ring=1)
+    out = pcbgpu.RolloutCollector(env, policy=lambda o: env.sample_random_actions(seed=1), horizon=4).collect()
+    assert out["obs"]["grid"].shape == (5, 32, 16, 16)
+    env.close()
+
+
+def test_errors_are_loud():
+    import pcbgpu
+    from pcbgpu._lib import PcbError
+
+    env = make("C", 4)
+    with pytest.raises(ValueError):
+        env.step(torch.zeros((4, 2), dtype=torch.int32))
+    with pytest.raises(PcbError, match="n_comp"):
+        env.set_instances([dict(comp_h=np.zeros(0), comp_w=np.zeros(0), pin_comp=np.zeros(0),
+                                pin_rx=np.zeros(0), pin_ry=np.zeros(0), pin_net=np.zeros(0),
+                                pin_id=np.zeros(0), n_nets=0)])
+    env.close()
+    with pytest.raises(PcbError, match="grid"):
+        pcbgpu.PcbVecEnv(dict(CONFIGS["A"], height=80, width=80), 4)
