@@ -250,7 +250,7 @@ class PinEnv:
         f = np.array([h, w, x, y, (h * w) / self.area])
         if self.spatial:
             ids = np.full(self.max_num_pins_per_component, -1)
-            mine = self.inst.pin_id[self.inst.pin_comp == c]
+            mine = self.inst.pin_id[self._comp_pins[c]]
             ids[: len(mine)] = mine
             f = np.append(f, ids)
         return f
@@ -261,7 +261,7 @@ class PinEnv:
         overwrite earlier ones when (component, pin_id) repeats."""
         I = self.inst
         for c in range(I.n_comp):
-            for p in np.flatnonzero(I.pin_comp == c):
+            for p in self._comp_pins[c]:
                 row = [self.rel[p][0], self.rel[p][1], self.abs[p][0], self.abs[p][1]]
                 if self.spatial:
                     self.all_pins_num_feature[I.pin_id[p], :] = row
@@ -304,6 +304,12 @@ class PinEnv:
         self.grid = np.zeros((self.height, self.width))
         self.inst = I = instance if instance is not None else generate_pin(self.cfg, self.spatial)
         self.pos = [(-1, -1)] * I.n_comp
+        # component.pins / net_pins[net]: pin indices in env.pins order (pin:1029-1035, 1166-1169)
+        self._comp_pins = [[] for _ in range(I.n_comp)]
+        self._net_pins = [[] for _ in range(I.n_nets)]
+        for p in range(I.n_pins):
+            self._comp_pins[int(I.pin_comp[p])].append(p)
+            self._net_pins[int(I.pin_net[p])].append(p)
         self.rel = [(int(I.pin_rx[p]), int(I.pin_ry[p])) for p in range(I.n_pins)]
         self.abs = [(-1, -1)] * I.n_pins
         if self.spatial:
@@ -340,7 +346,7 @@ class PinEnv:
         ph, pw = (h, w) if o in (0, 2) else (w, h)
         self.grid[x:x + ph, y:y + pw] = 1
         self.pos[c] = (x, y)
-        for p in np.flatnonzero(I.pin_comp == c):
+        for p in self._comp_pins[c]:
             rx, ry = self.rel[p]
             if o == 1:
                 rx, ry = ry, h - rx - 1
@@ -385,8 +391,7 @@ class PinEnv:
 
     # ---- reward -------------------------------------------------------------
     def net_positions(self):  # get_net_pin_positions :1266-1280
-        I = self.inst
-        return [[self.abs[p] for p in np.flatnonzero(I.pin_net == n)] for n in range(I.n_nets)]
+        return [[self.abs[p] for p in pins] for pins in self._net_pins]
 
     def normalizers(self):  # :879-896
         c = self.cfg
