@@ -260,13 +260,12 @@ def gpu_arm(args, rank, world, local_rank):
         return
     peak, peak_src = load_peaks()
     step_ms, step_n = kt["step"]
-    term_ms, term_n = kt["terminal"]
+    term_ms, term_n = kt["reward"]
     samp_ms, samp_n = kt["sample"]
     done_frac = stats2["episodes"] / (float(N) * K)
     # with the fused terminal path (centroid reward) the step kernel also writes the first
     # observation of every restarting env; otherwise terminal_kernel writes those
-    fused = term_n == 0
-    written = float(N) if fused else N * (1.0 - done_frac)
+    written = float(N)  # step_kernel writes every env's observation (restarting envs included)
     bytes_per_launch = ALGO_BYTES[name] * written
     avg_step_s = step_ms * 1e-3 / max(step_n, 1)
     achieved = bytes_per_launch / avg_step_s / 1e9
@@ -301,7 +300,7 @@ def gpu_arm(args, rank, world, local_rank):
                      "envs_written_per_launch": written,
                      "avg_launch_us": avg_step_s * 1e6,
                      "whole_step_frac": value / world * ALGO_BYTES[name] / 1e9 / peak,
-                     "kernel_share_ms": {"step": step_ms, "terminal": term_ms, "sample": samp_ms}},
+                     "kernel_share_ms": {"step": step_ms, "reward": term_ms, "sample": samp_ms}},
         "episodes": {"device_pass": stats["episodes"], "timed_kernel_pass": stats2["episodes"],
                      "e2e_pass": stats3["episodes"],
                      "mean_return": stats["sum_return"] / max(stats["episodes"], 1),

@@ -180,7 +180,7 @@ int pcb_rollout_random(pcb_env_t* env, uint64_t seed, int n_steps, int32_t* d_ac
 
 /* Measurement aid: when on, every kernel launch is bracketed by CUDA events on the
  * launching stream.  pcb_kernel_times waits for them and returns the summed device
- * time [ms] and launch count per kernel {step, terminal, reset, sample}, then clears. */
+ * time [ms] and launch count per kernel {step, reward, reset, sample}, then clears. */
 int pcb_enable_kernel_timing(pcb_env_t* env, int on);
 int pcb_kernel_times(pcb_env_t* env, double ms[4], int64_t launches[4]);
 

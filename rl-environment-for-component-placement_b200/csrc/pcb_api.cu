@@ -73,7 +73,10 @@ struct pcb_env {
   int32_t* d_actions2;
   float* ratio_lut;
   int shape_id;        // 0 = generic (DynShape), 1..4 = ShapeB/C/D/E
-  bool fuse;           // step_kernel finishes episodes itself
+  uint8_t* jobs;       // routing jobs (pin kinds)
+  uint32_t* job_count; // [2]
+  size_t reward_smem;
+  int reward_grid;
   std::vector<TensorDesc> tensors;
   std::vector<void*> allocs;
   // optional per-kernel CUDA-event timing (pcb_enable_kernel_timing)
@@ -120,7 +123,8 @@ Params make_params(const pcb_env* e) {
   p.stats = e->stats;
   p.step_no = e->step_no;
   p.ratio_lut = e->ratio_lut;
-  p.fuse_terminal = e->fuse ? 1 : 0;
+  p.jobs = e->jobs;
+  p.job_count = e->job_count;
   return p;
 }
 
@@ -173,8 +177,9 @@ int launch(pcb_env* e, KernelId id, const Params& p, cudaStream_t st) {
     CU(cudaEventRecord(tm.a, st));
   }
   if (id == K_TERM) {
-    if (e->wide) terminal_kernel<2, uint64_t><<<grid, block, sm, st>>>(p);
-    else terminal_kernel<1, uint32_t><<<grid, block, sm, st>>>(p);
+    dim3 rgrid(e->reward_grid);
+    if (e->d.reward_type == PCB_REWARD_CENTROID) reward_kernel<false><<<rgrid, block, e->reward_smem, st>>>(p);
+    else reward_kernel<true><<<rgrid, block, e->reward_smem, st>>>(p);
   } else if (id == K_SAMPLE) {
     if (e->wide) sample_kernel<2, uint64_t><<<grid, block, sm, st>>>(p);
     else sample_kernel<1, uint32_t><<<grid, block, sm, st>>>(p);
@@ -379,14 +384,13 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
   e->shape_id = cfg->reserved0 == 1 ? 0 : pick_shape(e->d);  // reserved0 == 1 forces the generic kernels (tests)
   if (e->shape_id) fill_dims(*cfg, true, e->d);  // every FixedShape expands boards from registers
   const Dims& d = e->d;
-  e->smem_bytes = (size_t)d.L.sm_stride * kWarpsPerCta;
+  e->smem_bytes = (size_t)kLutBytes + (size_t)d.L.sm_stride * kWarpsPerCta;
   if (e->smem_bytes > 200 * 1024) {
     delete e;
     return fail(PCB_ERR_INVALID, "configuration needs %zu bytes of shared memory per CTA", e->smem_bytes);
   }
   auto cleanup = [&](int code) { pcb_destroy(e); return code; };
 #define TRY(x) do { int rc_ = (x); if (rc_) return cleanup(rc_); } while (0)
-  e->fuse = d.kind < 2 || d.reward_type == PCB_REWARD_CENTROID;
   switch (e->shape_id) {
     case 1: TRY((set_smem_shape<1, uint32_t, ShapeB>(e->smem_bytes))); break;
     case 2: TRY((set_smem_shape<1, uint32_t, ShapeC>(e->smem_bytes))); break;
@@ -396,14 +400,26 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
       if (e->wide) TRY((set_smem_shape<2, uint64_t, DynShape>(e->smem_bytes)));
       else TRY((set_smem_shape<1, uint32_t, DynShape>(e->smem_bytes)));
   }
-  if (e->wide) TRY(set_smem(terminal_kernel<2, uint64_t>, e->smem_bytes));
-  else TRY(set_smem(terminal_kernel<1, uint32_t>, e->smem_bytes));
+  e->jobs = nullptr; e->job_count = nullptr; e->reward_smem = 0; e->reward_grid = 1;
+  if (d.kind >= 2) {
+    e->reward_smem = (size_t)((route_scratch_bytes(d.max_pins, d.K) + 15) & ~15) * kWarpsPerCta;
+    TRY(set_smem(reward_kernel<false>, e->reward_smem));
+    TRY(set_smem(reward_kernel<true>, e->reward_smem));
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    int want = (num_envs + kWarpsPerCta - 1) / kWarpsPerCta;
+    e->reward_grid = std::max(1, std::min(want, sms * 8));
+  }
   const size_t N = (size_t)num_envs, R = (size_t)e->ring;
   const int64_t n64 = num_envs, r64 = e->ring;
   TRY(dev_alloc(e, &e->state, N * d.L.st_stride));
   TRY(dev_alloc(e, &e->stats, kStatSlots * 8 * sizeof(double)));
   TRY(dev_alloc(e, &e->d_actions, N * 3 * sizeof(int32_t)));
   TRY(dev_alloc(e, &e->d_actions2, N * 3 * sizeof(int32_t)));
+  if (d.kind >= 2) {
+    TRY(dev_alloc(e, &e->jobs, N * (size_t)job_stride(d.max_pins)));
+    TRY(dev_alloc(e, &e->job_count, 2 * sizeof(uint32_t)));
+  }
   {
     // area ratio h*w/(H*W): float64 quotient rounded to float32, i.e. np.float32(reference value)
     const int nlut = d.mh * d.mw + 1;
@@ -514,6 +530,7 @@ int pcb_reset(pcb_env_t* e, const uint8_t* d_reset_mask, void* stream) {
     e->slice = 0;
     e->step_no = 0;
     CU(cudaMemsetAsync(e->stats, 0, kStatSlots * 8 * sizeof(double), st));
+    if (e->job_count) CU(cudaMemsetAsync(e->job_count, 0, 2 * sizeof(uint32_t), st));
   }
   Params p = make_params(e);
   p.reset_mask = d_reset_mask;
@@ -538,7 +555,7 @@ static int step_impl(pcb_env_t* e, const int32_t* d_actions, int action_format, 
   p.actions_out = d_next_actions;
   rc = launch(e, K_STEP, p, st);
   if (rc) return rc;
-  if (!e->fuse) rc = launch(e, K_TERM, p, st);
+  if (e->d.kind >= 2) rc = launch(e, K_TERM, p, st);  // routing rewards of the episodes that ended
   e->step_no += 1;
   return rc;
 }

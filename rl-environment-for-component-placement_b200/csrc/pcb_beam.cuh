@@ -125,9 +125,8 @@ __device__ __forceinline__ bool beam_less(const BeamItem& a, const BeamItem& b, 
 }
 
 // Routes every net; fills rs.start[net] and rs.nxt[pin] (global pin indices).
-template <typename T>
-__device__ __noinline__ void beam_paths(const Dims& d, const Env<T>& e, const RouteScratch& rs,
-                                        int lane, int n_nets) {
+__device__ __noinline__ void beam_paths(const Dims& d, const RouteScratch& rs, int lane,
+                                        int n_nets) {
   const int bw = d.beam_width;
   for (int net = lane; net < n_nets; net += 32) {
     const int lo = rs.net_off[net], m_all = rs.net_off[net + 1] - lo;
@@ -220,10 +219,8 @@ __device__ __noinline__ void beam_paths(const Dims& d, const Env<T>& e, const Ro
 }
 
 // crossings + wirelength of the beam route: segment headed by pin q = (q, nxt[q])
-template <typename T>
-__device__ __forceinline__ void beam_route(const Dims& d, const Env<T>& e, const RouteScratch& rs,
-                                           int lane, int n_pins, int n_nets, int& crossings,
-                                           double& wl) {
+__device__ __forceinline__ void beam_route(const Dims& d, const RouteScratch& rs, int lane,
+                                           int n_pins, int n_nets, int& crossings, double& wl) {
   for (int q = lane; q < n_pins; q += 32) {
     const int nx = rs.nxt[q];
     double x2 = 0.0, y2 = 0.0, len = -1.0;
@@ -237,7 +234,7 @@ __device__ __forceinline__ void beam_route(const Dims& d, const Env<T>& e, const
     rs.x2[q] = x2; rs.y2[q] = y2; rs.box[q] = box; rs.dist[q] = len;
   }
   __syncwarp();
-  crossings = count_crossings<T>(e, rs, lane, n_pins);
+  crossings = count_crossings(rs, lane, n_pins);
   // find_wirelength: nets in order, segments in path order, sequential float64 sum
   double acc = 0.0;
   if (lane == 0) {

@@ -258,9 +258,33 @@ struct BoardPath<FixedShape<KIND, HH, WW, CC, MH, MW, KK, MP>> {
   static constexpr bool fast = FixedShape<KIND, HH, WW, CC, MH, MW, KK, MP>::fast_board;
 };
 
+#ifndef PCB_OPT_LUT
+#define PCB_OPT_LUT 1
+#endif
+constexpr int kLutBytes = PCB_OPT_LUT ? 256 * 8 : 0;  // CTA-wide byte-expansion table
+
+// 8 bits -> 8 bytes of 0/1, one shared-memory load (table built once per CTA)
+__device__ __forceinline__ void build_expand_lut(uint8_t* smem) {
+#if PCB_OPT_LUT
+  uint2* lut = reinterpret_cast<uint2*>(smem);
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = make_uint2(spread4(i & 15), spread4(i >> 4));
+  __syncthreads();
+#endif
+}
+
+__device__ __forceinline__ uint4 expand16(const uint2* lut, uint32_t b) {
+#if PCB_OPT_LUT
+  uint2 lo = lut[b & 0xffu], hi = lut[(b >> 8) & 0xffu];
+  return make_uint4(lo.x, lo.y, hi.x, hi.y);
+#else
+  return spread16(b & 0xffffu);
+#endif
+}
+
 template <int RPL, typename T, typename S>
 __device__ __forceinline__ void write_board(const S& sh, uint8_t* dst, const T (&regs)[RPL],
-                                            const T* rows, int lane, int dup_off) {
+                                            const T* rows, int lane, int dup_off,
+                                            const uint2* lut) {
   uint4* d4 = reinterpret_cast<uint4*>(dst);
   uint4* e4 = reinterpret_cast<uint4*>(dst + dup_off);
   if constexpr (BoardPath<S>::fast) {
@@ -269,13 +293,13 @@ __device__ __forceinline__ void write_board(const S& sh, uint8_t* dst, const T (
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           uint32_t w = __shfl_sync(kFull, regs[0], (lane >> 1) + 16 * half);
-          uint4 v = spread16((w >> (16 * (lane & 1))) & 0xffffu);
+          uint4 v = expand16(lut, w >> (16 * (lane & 1)));
           d4[half * 32 + lane] = v;
           if (dup_off) e4[half * 32 + lane] = v;
         }
       } else {  // 16x16: one 16-byte chunk per row
         if (lane < 16) {
-          uint4 v = spread16((uint32_t)regs[0] & 0xffffu);
+          uint4 v = expand16(lut, (uint32_t)regs[0]);
           d4[lane] = v;
           if (dup_off) e4[lane] = v;
         }
@@ -284,7 +308,7 @@ __device__ __forceinline__ void write_board(const S& sh, uint8_t* dst, const T (
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         T w = __shfl_sync(kFull, regs[i >> 2], (i & 3) * 8 + (lane >> 2));
-        uint4 v = spread16((uint32_t)(w >> (16 * (lane & 3))) & 0xffffu);
+        uint4 v = expand16(lut, (uint32_t)(w >> (16 * (lane & 3))));
         d4[i * 32 + lane] = v;
         if (dup_off) e4[i * 32 + lane] = v;
       }
@@ -364,6 +388,24 @@ __device__ __forceinline__ uint32_t philox_u32(uint64_t seed, uint32_t c0, uint3
   return x0;
 }
 
+#ifndef PCB_OPT_RNG
+#define PCB_OPT_RNG 1
+#endif
+// 1: SplitMix64 finaliser of the 64-bit counter (seed, env, step) -- ~3x fewer
+// instructions than Philox4x32-10 (0), same counter-based, stateless construction.
+__device__ __forceinline__ uint32_t action_rand(uint64_t seed, uint32_t env, uint64_t step_no) {
+#if PCB_OPT_RNG
+  uint64_t z = seed + ((step_no << 32) | (uint64_t)env) * 0x9E3779B97F4A7C15ull;
+  z ^= step_no >> 32;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (uint32_t)(z >> 32);
+#else
+  return philox_u32(seed, env, (uint32_t)step_no, (uint32_t)(step_no >> 32));
+#endif
+}
+
 template <int RPL, typename T, typename S>
 __device__ __forceinline__ void sample_action(const S& sh, const T (&m0)[RPL], const T (&m1)[RPL],
                                               uint64_t seed, int env, uint64_t step_no, int lane,
@@ -377,7 +419,7 @@ __device__ __forceinline__ void sample_action(const S& sh, const T (&m0)[RPL], c
   const int total = O == 4 ? 2 * per_pair : (O == 2 ? per_pair : tot0);
   int ao = 0, ax = 0, ay = 0;
   if (total > 0) {
-    uint32_t r = philox_u32(seed, (uint32_t)env, (uint32_t)step_no, (uint32_t)(step_no >> 32));
+    uint32_t r = action_rand(seed, (uint32_t)env, step_no);
     int kth = (int)__umulhi(r, (uint32_t)total);  // uniform in [0, total)
     int obase = 0;
     if (O == 4 && kth >= per_pair) { kth -= per_pair; obase = 2; }
@@ -445,10 +487,13 @@ __device__ __forceinline__ void write_obs(const S& sh, const Params& p, Env<T>& 
   }
   const int HW = sh.H() * sh.W();
   const int O = sh.O();
-  write_board<RPL, T, S>(sh, p.out.grid + (size_t)env * sh.grid_b(), occ, e.occ, lane, 0);
+  extern __shared__ __align__(16) uint8_t smem_base[];
+  const uint2* lut = reinterpret_cast<const uint2*>(smem_base);
+  write_board<RPL, T, S>(sh, p.out.grid + (size_t)env * sh.grid_b(), occ, e.occ, lane, 0, lut);
   uint8_t* mk = p.out.mask + (size_t)env * sh.mask_b();
-  write_board<RPL, T, S>(sh, mk, m0, e.mrow, lane, O == 4 ? 2 * HW : 0);
-  if (O >= 2) write_board<RPL, T, S>(sh, mk + HW, m1, e.mrow + rows, lane, O == 4 ? 2 * HW : 0);
+  write_board<RPL, T, S>(sh, mk, m0, e.mrow, lane, O == 4 ? 2 * HW : 0, lut);
+  if (O >= 2)
+    write_board<RPL, T, S>(sh, mk + HW, m1, e.mrow + rows, lane, O == 4 ? 2 * HW : 0, lut);
   const int kind = sh.kind();
   if (kind == 0) return;
 
@@ -684,6 +729,7 @@ struct RouteScratch {
   uint16_t* nxt;      // beam route: next pin on the path, 0xFFFF = path end
   uint16_t* net_off;  // [K + 1] first pin of each net (pins are net-major)
   uint16_t* start;    // [K] beam route: first pin of the path
+  uint8_t* net;       // [max_pins] net of pin q
 };
 
 __device__ __forceinline__ RouteScratch route_scratch(uint8_t* scr, int max_pins, int K) {
@@ -700,7 +746,8 @@ __device__ __forceinline__ RouteScratch route_scratch(uint8_t* scr, int max_pins
   r.py = reinterpret_cast<int16_t*>(q); q += max_pins * 2;
   r.nxt = reinterpret_cast<uint16_t*>(q); q += max_pins * 2;
   r.net_off = reinterpret_cast<uint16_t*>(q); q += (K + 1) * 2;
-  r.start = reinterpret_cast<uint16_t*>(q);
+  r.start = reinterpret_cast<uint16_t*>(q); q += K * 2;
+  r.net = q;
   return r;
 }
 
@@ -717,15 +764,14 @@ __device__ __forceinline__ bool boxes_touch(uint32_t a, uint32_t b) {
 }
 
 // positions, net ranges, centroids (get_net_pin_positions pin:1266-1280, get_centroid :1282-1294)
-template <typename T>
-__device__ __forceinline__ void route_prepare(const Env<T>& e, const RouteScratch& rs, int lane,
+__device__ __forceinline__ void route_prepare(const JobPin* pins, const RouteScratch& rs, int lane,
                                               int n_pins, int n_nets) {
   for (int q = lane; q < n_pins; q += 32) {
-    PinRec pr = e.pins[q];
-    CompRec r = e.comps[pr.comp];
-    rs.px[q] = (int16_t)(r.x + pr.rx);
-    rs.py[q] = (int16_t)(r.y + pr.ry);
-    if (q == 0 || e.pins[q - 1].net != pr.net) rs.net_off[pr.net] = (uint16_t)q;
+    JobPin jp = pins[q];
+    rs.px[q] = jp.x;
+    rs.py[q] = jp.y;
+    rs.net[q] = jp.net;
+    if (q == 0 || pins[q - 1].net != jp.net) rs.net_off[jp.net] = (uint16_t)q;
   }
   if (lane == 0) rs.net_off[n_nets] = (uint16_t)n_pins;
   __syncwarp();
@@ -743,9 +789,7 @@ __device__ __forceinline__ void route_prepare(const Env<T>& e, const RouteScratc
 // segment t and walks the segments s of earlier nets; pairs whose integer boxes do
 // not touch cannot intersect (the reference requires the point inside both boxes),
 // the others are queued and tested 32 at a time with the reference's float64 formula.
-template <typename T>
-__device__ __forceinline__ int count_crossings(const Env<T>& e, const RouteScratch& rs, int lane,
-                                               int n_pins) {
+__device__ __forceinline__ int count_crossings(const RouteScratch& rs, int lane, int n_pins) {
   int cnt = 0, qn = 0;
   auto heavy = [&](uint32_t pr) -> int {
     int s = pr >> 16, t = pr & 0xffffu;
@@ -758,7 +802,7 @@ __device__ __forceinline__ int count_crossings(const Env<T>& e, const RouteScrat
     int my_hi = 0;
     if (t < n_pins) {
       mine = rs.box[t];
-      if (mine != kNoBox) my_hi = rs.net_off[e.pins[t].net];  // segments of earlier nets only
+      if (mine != kNoBox) my_hi = rs.net_off[rs.net[t]];  // segments of earlier nets only
     }
     const int smax = __reduce_max_sync(kFull, my_hi);
     for (int s = 0; s < smax; ++s) {
@@ -784,12 +828,10 @@ __device__ __forceinline__ int count_crossings(const Env<T>& e, const RouteScrat
 
 // Centroid route (route_pins_centroid, pin:1296-1324): segment headed by pin q =
 // (pin q, centroid of its net); a 2-pin net has the single segment (pin 0, pin 1).
-template <typename T>
-__device__ __forceinline__ void centroid_route(const Dims& d, const Env<T>& e,
-                                               const RouteScratch& rs, int lane, int n_pins,
-                                               int& crossings, double& wl) {
+__device__ __forceinline__ void centroid_route(const Dims& d, const RouteScratch& rs, int lane,
+                                               int n_pins, int& crossings, double& wl) {
   for (int q = lane; q < n_pins; q += 32) {
-    const int net = e.pins[q].net;
+    const int net = rs.net[q];
     const int lo = rs.net_off[net], cnt = rs.net_off[net + 1] - lo;
     double x2 = 0.0, y2 = 0.0, len = -1.0;
     uint32_t box = kNoBox;
@@ -803,7 +845,7 @@ __device__ __forceinline__ void centroid_route(const Dims& d, const Env<T>& e,
     rs.x2[q] = x2; rs.y2[q] = y2; rs.box[q] = box; rs.dist[q] = len;
   }
   __syncwarp();
-  crossings = count_crossings<T>(e, rs, lane, n_pins);
+  crossings = count_crossings(rs, lane, n_pins);
   // find_wirelength (pin:741-759): the reference's sequential float64 sum, net by net
   double acc = 0.0;
   if (lane == 0)
@@ -821,44 +863,38 @@ __device__ __forceinline__ void centroid_route(const Dims& d, const Env<T>& e,
 
 namespace pcb {
 
-// End of an episode: routing reward when everything is placed (pin kinds), episode
-// statistics, and with auto-reset the next instance + its first observation.
-// BEAM = false compiles the beam router out (the fused path of step_kernel).
-template <int RPL, typename T, typename S, bool BEAM>
+// End of an episode inside step_kernel: episode statistics (or, when the routing reward
+// is still to be computed, a job for reward_kernel), and with auto-reset the next
+// instance from the bank plus its first observation.
+template <int RPL, typename T, typename S>
 __device__ __forceinline__ void finish_episode(const S& sh, const Params& p, Env<T>& e, int env,
-                                               int lane, double reward_in, uint8_t* gstate) {
+                                               int lane, double reward, bool route,
+                                               uint8_t* gstate) {
   const Dims& d = p.d;
   const int kind = sh.kind();
-  const int n_comp = e.hdr->n_comp, n_pins = e.hdr->n_pins, n_nets = e.hdr->n_nets;
-  double reward = reward_in, wl = 0.0, ni = 0.0;
-  const bool route = kind >= 2 && e.hdr->cur == n_comp;
-  if (route) {
-    RouteScratch rs = route_scratch(e.scr, sh.max_pins(), sh.K());
-    route_prepare<T>(e, rs, lane, n_pins, n_nets);
-    int crossings = 0;
-    double length = 0.0;
-    if (!BEAM || d.reward_type == 0) {
-      centroid_route<T>(d, e, rs, lane, n_pins, crossings, length);
-    } else if constexpr (BEAM) {
-      beam_paths<T>(d, e, rs, lane, n_nets);
-      beam_route<T>(d, e, rs, lane, n_pins, n_nets, crossings, length);
-      if (d.reward_type == 2) {  // "both": fewer crossings wins, beam on ties (pin:643-661)
-        int c2; double l2;
-        centroid_route<T>(d, e, rs, lane, n_pins, c2, l2);
-        if (c2 < crossings) { crossings = c2; length = l2; }
-      }
-    }
-    wl = length / d.wl_norm;            // pin:921 / 940 / 959-961
-    ni = (double)crossings / d.ni_norm; // pin:922-924
-    reward = -1.0 * (d.ww * wl + d.wi * ni);
-    if (lane == 0) { p.out.reward[env] = reward; p.out.wl[env] = wl; p.out.ni[env] = ni; }
-  } else if (kind >= 2) {
-    wl = d.pen_wl; ni = d.pen_ni;
-  }
-
   const bool first_report = !(e.hdr->flags & kFlagFinished);
-  if (lane == 0) {
-    double ret = e.dyn->ep_return + (route ? reward : 0.0);
+  if (route) {
+    // all components placed: find_reward needs the routes -> leave the pin positions
+    const int n_pins = e.hdr->n_pins;
+    uint32_t idx = 0;
+    if (lane == 0) idx = atomicAdd(p.job_count + (p.step_no & 1), 1u);
+    idx = __shfl_sync(kFull, idx, 0);
+    uint8_t* job = p.jobs + (size_t)idx * job_stride(sh.max_pins());
+    if (lane == 0) {
+      RouteJob j;
+      j.env = (uint32_t)env; j.n_pins = (uint16_t)n_pins; j.n_nets = e.hdr->n_nets;
+      j.count_stats = first_report ? 1 : 0; j.ep_len = e.hdr->ep_len; j.pad = 0;
+      j.ep_return = e.dyn->ep_return; j.pad2 = 0.0;
+      *reinterpret_cast<RouteJob*>(job) = j;
+    }
+    JobPin* jp = reinterpret_cast<JobPin*>(job + 32);
+    for (int q = lane; q < n_pins; q += 32) {
+      PinRec pr = e.pins[q];
+      CompRec r = e.comps[pr.comp];
+      jp[q] = JobPin{(uint8_t)(r.x + pr.rx), (uint8_t)(r.y + pr.ry), pr.net, 0};
+    }
+  } else if (lane == 0) {
+    double ret = e.dyn->ep_return;
     p.out.ep_return[env] = ret;
     p.out.ep_length[env] = (int32_t)e.hdr->ep_len;
     if (first_report) {
@@ -866,7 +902,7 @@ __device__ __forceinline__ void finish_episode(const S& sh, const Params& p, Env
       atomicAdd(st + 0, 1.0);
       atomicAdd(st + 1, ret);
       atomicAdd(st + 2, (double)e.hdr->ep_len);
-      if (kind >= 2) { atomicAdd(st + 3, wl); atomicAdd(st + 4, ni); }
+      if (kind >= 2) { atomicAdd(st + 3, d.pen_wl); atomicAdd(st + 4, d.pen_ni); }
     }
   }
   __syncwarp();
@@ -898,14 +934,16 @@ __device__ __forceinline__ void finish_episode(const S& sh, const Params& p, Env
 // K1/K2/K3 (+ fused K4/K6/K7): step
 // ---------------------------------------------------------------------------
 template <int RPL, typename T, typename S>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, PCB_MIN_BLOCKS) step_kernel(const Params p) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, PCB_MIN_BLOCKS)
+step_kernel(const Params p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const Dims& d = p.d;
   const S sh(d);
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const int env = blockIdx.x * kWarpsPerCta + wic;
+  build_expand_lut(smem);
   if (env >= p.n_envs) return;
-  Env<T> e(smem + (size_t)wic * sh.sm_stride(), sh);
+  Env<T> e(smem + kLutBytes + (size_t)wic * sh.sm_stride(), sh);
   uint8_t* gstate = p.state + (size_t)env * sh.st_stride();
   copy16(e.sm, gstate, sh.st_stride(), lane);
 
@@ -998,7 +1036,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, PCB_MIN_BLOCKS) step_kernel
   }
   __syncwarp();
   const bool restart = done && d.autoreset;
-  if (!(restart && p.fuse_terminal)) {  // a restarting env overwrites its state below
+  if (!restart) {  // a restarting env overwrites its state below
     uint4* g4 = reinterpret_cast<uint4*>(gstate);
     const uint4* s4 = reinterpret_cast<const uint4*>(e.sm);
     if (lane < 2) g4[lane] = s4[lane];
@@ -1018,26 +1056,60 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, PCB_MIN_BLOCKS) step_kernel
       if (kind >= 2 && done) { p.out.wl[env] = d.pen_wl; p.out.ni[env] = d.pen_ni; }
     }
   }
-  if (done && p.fuse_terminal)
-    finish_episode<RPL, T, S, false>(sh, p, e, env, lane, reward, gstate);
+  if (done) finish_episode<RPL, T, S>(sh, p, e, env, lane, reward, route, gstate);
 }
 
-// K4 + K6 as a separate launch (beam / both reward types): a warp whose environment
-// did not finish exits at once.
-template <int RPL, typename T>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) terminal_kernel(const Params p) {
+// K4: the routing reward (find_reward, pin:832-975) of the episodes that finished in this
+// step with every component placed.  A small persistent grid walks the job list that
+// step_kernel left; one warp per job.  BEAM = true adds the beam-search router
+// (reward types "beam" / "both"), which needs far more registers.
+template <bool BEAM>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) reward_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const Dims& d = p.d;
-  const DynShape sh(d);
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
-  const int env = blockIdx.x * kWarpsPerCta + wic;
-  if (env >= p.n_envs) return;
-  if (!p.out.done[env]) return;
-  Env<T> e(smem + (size_t)wic * sh.sm_stride(), sh);
-  uint8_t* gstate = p.state + (size_t)env * sh.st_stride();
-  copy16(e.sm, gstate, sh.st_stride(), lane);
-  __syncwarp();
-  finish_episode<RPL, T, DynShape, true>(sh, p, e, env, lane, p.out.reward[env], gstate);
+  const int gw = blockIdx.x * kWarpsPerCta + wic, nw = gridDim.x * kWarpsPerCta;
+  const uint32_t count = p.job_count[p.step_no & 1];
+  if (gw == 0 && lane == 0) p.job_count[(p.step_no & 1) ^ 1] = 0;  // ready for the next step
+  const int scr_bytes = route_scratch_bytes(d.max_pins, d.K);
+  RouteScratch rs = route_scratch(smem + (size_t)wic * ((scr_bytes + 15) & ~15), d.max_pins, d.K);
+  for (uint32_t j = gw; j < count; j += nw) {
+    const uint8_t* job = p.jobs + (size_t)j * job_stride(d.max_pins);
+    const RouteJob hdr = *reinterpret_cast<const RouteJob*>(job);
+    const int n_pins = hdr.n_pins, n_nets = hdr.n_nets, env = (int)hdr.env;
+    route_prepare(reinterpret_cast<const JobPin*>(job + 32), rs, lane, n_pins, n_nets);
+    int crossings = 0;
+    double length = 0.0;
+    if (!BEAM || d.reward_type == 0) {
+      centroid_route(d, rs, lane, n_pins, crossings, length);
+    } else if constexpr (BEAM) {
+      beam_paths(d, rs, lane, n_nets);
+      beam_route(d, rs, lane, n_pins, n_nets, crossings, length);
+      if (d.reward_type == 2) {  // "both": fewer crossings wins, beam on ties (pin:643-661)
+        int c2; double l2;
+        centroid_route(d, rs, lane, n_pins, c2, l2);
+        if (c2 < crossings) { crossings = c2; length = l2; }
+      }
+    }
+    const double wl = length / d.wl_norm;             // pin:921 / 940 / 959-961
+    const double ni = (double)crossings / d.ni_norm;  // pin:922-924
+    const double reward = -1.0 * (d.ww * wl + d.wi * ni);
+    if (lane == 0) {
+      const double ret = hdr.ep_return + reward;
+      p.out.reward[env] = reward; p.out.wl[env] = wl; p.out.ni[env] = ni;
+      p.out.ep_return[env] = ret;
+      p.out.ep_length[env] = (int32_t)hdr.ep_len;
+      if (hdr.count_stats) {
+        double* st = p.stats + (size_t)(env & (kStatSlots - 1)) * 8;
+        atomicAdd(st + 0, 1.0);
+        atomicAdd(st + 1, ret);
+        atomicAdd(st + 2, (double)hdr.ep_len);
+        atomicAdd(st + 3, wl);
+        atomicAdd(st + 4, ni);
+      }
+    }
+    __syncwarp();
+  }
 }
 
 // K6: reset() -- all envs (reset_mask == nullptr) or the masked ones.
@@ -1048,9 +1120,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) reset_kernel(const Params p
   const S sh(d);
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const int env = blockIdx.x * kWarpsPerCta + wic;
+  build_expand_lut(smem);
   if (env >= p.n_envs) return;
   if (p.reset_mask && !p.reset_mask[env]) return;
-  Env<T> e(smem + (size_t)wic * sh.sm_stride(), sh);
+  Env<T> e(smem + kLutBytes + (size_t)wic * sh.sm_stride(), sh);
   uint8_t* gstate = p.state + (size_t)env * sh.st_stride();
   uint32_t slot = (uint32_t)env;
   uint64_t epno = 0;

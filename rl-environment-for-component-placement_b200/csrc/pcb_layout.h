@@ -86,7 +86,7 @@ PCB_HD constexpr int maxc(int a, int b) { return a > b ? a : b; }
 
 // terminal-reward scratch per warp: per-pin arrays + per-net arrays + pair queue
 PCB_HD constexpr int route_scratch_bytes(int max_pins, int K) {
-  return max_pins * (8 + 8 + 8 + 4 + 2 + 2 + 2) + K * (8 + 8 + 2 + 2) + 2 + kPairQueue * 4 + 64;
+  return max_pins * (8 + 8 + 8 + 4 + 2 + 2 + 2 + 1) + K * (8 + 8 + 2 + 2) + 2 + kPairQueue * 4 + 64;
 }
 
 // fast_board: the kernel expands bitboards straight from registers (FixedShape 16/32/64
@@ -117,12 +117,25 @@ PCB_HD constexpr Layout make_layout(int kind, int H, int W, int C, int mh, int m
   if (kind == 3) stage = maxc(maxc(stage, L.feat_n * 4), maxc(L.pgrid_b, L.cgrid_b));
   L.sm_mrow = L.st_stride;
   L.sm_stage = L.sm_mrow + (fast_board ? 0 : 2 * rows * word);
-  // the reward scratch and the observation staging area are never live together
-  L.sm_scr = L.sm_stage;
-  L.sm_stride = align16c(L.sm_stage + maxc(align16c(stage) + 16,
-                                           kind >= 2 ? route_scratch_bytes(max_pins, K) : 0));
+  L.sm_scr = L.sm_stage;  // (unused by the step kernel; the reward kernel has its own scratch)
+  L.sm_stride = align16c(L.sm_stage + align16c(stage) + 16);
   return L;
 }
+
+// A finished pin-env episode whose components are all placed leaves a routing job for
+// reward_kernel: the absolute pin positions (net-major) and the episode bookkeeping.
+struct __align__(16) RouteJob {
+  uint32_t env;
+  uint16_t n_pins;
+  uint8_t n_nets;
+  uint8_t count_stats;  // 0 when the episode was already reported (autoreset off, re-stepped)
+  uint32_t ep_len;
+  uint32_t pad;
+  double ep_return;     // return before the terminal reward
+  double pad2;
+};
+struct JobPin { uint8_t x, y, net, pad; };
+PCB_HD constexpr int job_stride(int max_pins) { return 32 + align16c(max_pins * 4); }
 
 // Everything a kernel needs to know about the configuration; passed by value.
 struct Dims {
@@ -164,7 +177,8 @@ struct Params {
   int action_format;
   const uint8_t* reset_mask;
   int reset_first;
-  int fuse_terminal;  // 1: step_kernel finishes episodes itself (no beam route needed)
+  uint8_t* jobs;        // [N][job_stride] routing jobs of the current step
+  uint32_t* job_count;  // [2] job counters, indexed by step parity
   double* stats;      // [kStatSlots][8]
   uint64_t seed;
   uint64_t step_no;

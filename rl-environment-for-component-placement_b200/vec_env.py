@@ -158,7 +158,7 @@ class PcbVecEnv:
         ms = (ctypes.c_double * 4)()
         n = (ctypes.c_int64 * 4)()
         _lib.check(self.lib.pcb_kernel_times(self._h, ms, n))
-        return {k: (ms[i], int(n[i])) for i, k in enumerate(("step", "terminal", "reset", "sample"))}
+        return {k: (ms[i], int(n[i])) for i, k in enumerate(("step", "reward", "reset", "sample"))}
 
     def step_host(self, actions_np, reward_np, done_np):
         """step() through host buffers (pcb_step_host): H2D actions, D2H reward/done."""
