@@ -154,11 +154,15 @@ int pcb_step_host(pcb_env_t* env, const int32_t* h_actions, int action_format,
  * all_components_feature, component_mask, placement_mask, all_pins_num_feature,
  * all_pins_cat_feature, pin_grid, component_grid) with shape [R, N, ...], and
  * reward, done, wirelength, num_intersections, episode_return, episode_length
- * with shape [N].  The deleter frees only the small manager struct. */
+ * with shape [2, N] (see pcb_current_result_half).  The deleter frees only the small manager struct. */
 int pcb_get_tensor(pcb_env_t* env, const char* key, DLManagedTensor** out);
 
 /* Index of the ring slice the last reset/step wrote. */
 int pcb_current_slice(pcb_env_t* env);
+
+/* reward, done, wirelength, num_intersections, episode_return, episode_length are
+ * double-buffered ([2, N]): the step that just ran wrote half pcb_current_result_half(). */
+int pcb_current_result_half(pcb_env_t* env);
 
 /* Episode statistics accumulated on device since the last clear:
  * out = {episodes, sum_return, sum_length, sum_wirelength, sum_intersections,

@@ -76,7 +76,11 @@ struct pcb_env {
   uint8_t* jobs;       // routing jobs (pin kinds)
   uint32_t* job_count; // [2]
   size_t reward_smem;
-  int reward_grid;
+  int reward_grid;       // reward_kernel grid when it runs alone
+  int reward_grid_side;  // ... when it overlaps the next step kernel (pcb_rollout_random)
+  cudaStream_t side;     // stream of the overlapped reward kernels
+  cudaEvent_t ev_step[2], ev_rew[2];
+  bool rew_pending[2];
   std::vector<TensorDesc> tensors;
   std::vector<void*> allocs;
   // optional per-kernel CUDA-event timing (pcb_enable_kernel_timing)
@@ -95,10 +99,12 @@ int set_smem(K kernel, size_t bytes) {
   return 0;
 }
 
-Out slice_ptrs(const pcb_env* e, int slice) {
+Out slice_ptrs(const pcb_env* e, int slice, int parity) {
   const Dims& d = e->d;
-  const size_t N = (size_t)e->n_envs, s = (size_t)slice;
+  const size_t N = (size_t)e->n_envs, s = (size_t)slice, q = (size_t)parity;
   Out o = e->base;
+  o.reward += q * N; o.done += q * N; o.wl += q * N; o.ni += q * N;
+  o.ep_return += q * N; o.ep_length += q * N;
   if (o.grid) o.grid += s * N * d.L.grid_b;
   if (o.mask) o.mask += s * N * d.L.mask_b;
   if (o.feat) o.feat += s * N * d.L.feat_n;
@@ -111,11 +117,14 @@ Out slice_ptrs(const pcb_env* e, int slice) {
   return o;
 }
 
-Params make_params(const pcb_env* e) {
+// step_no = index of the step about to run (or just reset): its scalars go to half
+// (step_no & 1); after a reset (no step yet) the "last written" half is 1.
+Params make_params(const pcb_env* e, bool for_reset = false) {
   Params p;
   memset(&p, 0, sizeof p);
   p.d = e->d;
-  p.out = slice_ptrs(e, e->slice);
+  const int parity = for_reset ? (int)((e->step_no + 1) & 1) : (int)(e->step_no & 1);
+  p.out = slice_ptrs(e, e->slice, parity);
   p.state = e->state;
   p.bank = e->bank;
   p.bank_count = e->bank_count;
@@ -123,7 +132,7 @@ Params make_params(const pcb_env* e) {
   p.stats = e->stats;
   p.step_no = e->step_no;
   p.ratio_lut = e->ratio_lut;
-  p.jobs = e->jobs;
+  p.jobs = e->jobs ? e->jobs + (size_t)parity * e->n_envs * job_stride(e->d.max_pins) : nullptr;
   p.job_count = e->job_count;
   return p;
 }
@@ -167,7 +176,7 @@ int set_smem_shape(size_t bytes) {
   return set_smem(reset_kernel<RPL, T, S>, bytes);
 }
 
-int launch(pcb_env* e, KernelId id, const Params& p, cudaStream_t st) {
+int launch(pcb_env* e, KernelId id, const Params& p, cudaStream_t st, int reward_grid = 0) {
   dim3 grid((e->n_envs + kWarpsPerCta - 1) / kWarpsPerCta), block(kWarpsPerCta * 32);
   size_t sm = id == K_SAMPLE ? 0 : e->smem_bytes;
   pcb_env::Timed tm{(int)id, nullptr, nullptr};
@@ -177,7 +186,7 @@ int launch(pcb_env* e, KernelId id, const Params& p, cudaStream_t st) {
     CU(cudaEventRecord(tm.a, st));
   }
   if (id == K_TERM) {
-    dim3 rgrid(e->reward_grid);
+    dim3 rgrid(reward_grid > 0 ? reward_grid : e->reward_grid);
     if (e->d.reward_type == PCB_REWARD_CENTROID) reward_kernel<false><<<rgrid, block, e->reward_smem, st>>>(p);
     else reward_kernel<true><<<rgrid, block, e->reward_smem, st>>>(p);
   } else if (id == K_SAMPLE) {
@@ -400,7 +409,9 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
       if (e->wide) TRY((set_smem_shape<2, uint64_t, DynShape>(e->smem_bytes)));
       else TRY((set_smem_shape<1, uint32_t, DynShape>(e->smem_bytes)));
   }
-  e->jobs = nullptr; e->job_count = nullptr; e->reward_smem = 0; e->reward_grid = 1;
+  e->jobs = nullptr; e->job_count = nullptr; e->reward_smem = 0; e->reward_grid = 1; e->reward_grid_side = 1;
+  e->side = nullptr; e->rew_pending[0] = e->rew_pending[1] = false;
+  for (int i = 0; i < 2; ++i) { e->ev_step[i] = nullptr; e->ev_rew[i] = nullptr; }
   if (d.kind >= 2) {
     e->reward_smem = (size_t)((route_scratch_bytes(d.max_pins, d.K) + 15) & ~15) * kWarpsPerCta;
     TRY(set_smem(reward_kernel<false>, e->reward_smem));
@@ -408,7 +419,22 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     int want = (num_envs + kWarpsPerCta - 1) / kWarpsPerCta;
-    e->reward_grid = std::max(1, std::min(want, sms * 8));
+#ifndef PCB_REWARD_GRID_MULT
+#define PCB_REWARD_GRID_MULT 16
+#endif
+    e->reward_grid = std::max(1, std::min(want, sms * PCB_REWARD_GRID_MULT));
+#ifndef PCB_REWARD_SIDE_MULT
+#define PCB_REWARD_SIDE_MULT 4
+#endif
+    e->reward_grid_side = std::max(1, std::min(want, sms * PCB_REWARD_SIDE_MULT));
+    int lo_pri = 0, hi_pri = 0;
+    cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+    cudaError_t se = cudaStreamCreateWithPriority(&e->side, cudaStreamNonBlocking, hi_pri);
+    for (int i = 0; i < 2 && se == cudaSuccess; ++i) {
+      se = cudaEventCreateWithFlags(&e->ev_step[i], cudaEventDisableTiming);
+      if (se == cudaSuccess) se = cudaEventCreateWithFlags(&e->ev_rew[i], cudaEventDisableTiming);
+    }
+    if (se != cudaSuccess) return cleanup(fail(PCB_ERR_CUDA, "side stream/events: %s", cudaGetErrorString(se)));
   }
   const size_t N = (size_t)num_envs, R = (size_t)e->ring;
   const int64_t n64 = num_envs, r64 = e->ring;
@@ -417,8 +443,8 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
   TRY(dev_alloc(e, &e->d_actions, N * 3 * sizeof(int32_t)));
   TRY(dev_alloc(e, &e->d_actions2, N * 3 * sizeof(int32_t)));
   if (d.kind >= 2) {
-    TRY(dev_alloc(e, &e->jobs, N * (size_t)job_stride(d.max_pins)));
-    TRY(dev_alloc(e, &e->job_count, 2 * sizeof(uint32_t)));
+    TRY(dev_alloc(e, &e->jobs, 2 * N * (size_t)job_stride(d.max_pins)));
+    TRY(dev_alloc(e, &e->job_count, 4 * sizeof(uint32_t)));
   }
   {
     // area ratio h*w/(H*W): float64 quotient rounded to float32, i.e. np.float32(reference value)
@@ -462,18 +488,18 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
       add("component_grid", (void**)&e->base.cgrid, kDLUInt, 8, {r64, n64, d.C, d.mh, d.mw, d.K}, true);
     }
   }
-  TRY(dev_alloc(e, &e->base.reward, N * sizeof(double)));
-  add("reward", (void**)&e->base.reward, kDLFloat, 64, {n64}, false);
-  TRY(dev_alloc(e, &e->base.done, N));
-  add("done", (void**)&e->base.done, kDLUInt, 8, {n64}, false);
-  TRY(dev_alloc(e, &e->base.wl, N * sizeof(double)));
-  add("wirelength", (void**)&e->base.wl, kDLFloat, 64, {n64}, false);
-  TRY(dev_alloc(e, &e->base.ni, N * sizeof(double)));
-  add("num_intersections", (void**)&e->base.ni, kDLFloat, 64, {n64}, false);
-  TRY(dev_alloc(e, &e->base.ep_return, N * sizeof(double)));
-  add("episode_return", (void**)&e->base.ep_return, kDLFloat, 64, {n64}, false);
-  TRY(dev_alloc(e, &e->base.ep_length, N * sizeof(int32_t)));
-  add("episode_length", (void**)&e->base.ep_length, kDLInt, 32, {n64}, false);
+  TRY(dev_alloc(e, &e->base.reward, 2 * N * sizeof(double)));
+  add("reward", (void**)&e->base.reward, kDLFloat, 64, {2, n64}, false);
+  TRY(dev_alloc(e, &e->base.done, 2 * N));
+  add("done", (void**)&e->base.done, kDLUInt, 8, {2, n64}, false);
+  TRY(dev_alloc(e, &e->base.wl, 2 * N * sizeof(double)));
+  add("wirelength", (void**)&e->base.wl, kDLFloat, 64, {2, n64}, false);
+  TRY(dev_alloc(e, &e->base.ni, 2 * N * sizeof(double)));
+  add("num_intersections", (void**)&e->base.ni, kDLFloat, 64, {2, n64}, false);
+  TRY(dev_alloc(e, &e->base.ep_return, 2 * N * sizeof(double)));
+  add("episode_return", (void**)&e->base.ep_return, kDLFloat, 64, {2, n64}, false);
+  TRY(dev_alloc(e, &e->base.ep_length, 2 * N * sizeof(int32_t)));
+  add("episode_length", (void**)&e->base.ep_length, kDLInt, 32, {2, n64}, false);
 #undef TRY
   *out = e;
   return 0;
@@ -482,6 +508,11 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
 int pcb_destroy(pcb_env_t* e) {
   if (!e) return 0;
   cudaSetDevice(e->device);
+  for (int i = 0; i < 2; ++i) {
+    if (e->ev_step[i]) cudaEventDestroy(e->ev_step[i]);
+    if (e->ev_rew[i]) cudaEventDestroy(e->ev_rew[i]);
+  }
+  if (e->side) cudaStreamDestroy(e->side);
   for (void* p : e->allocs) cudaFree(p);
   if (e->bank) cudaFree(e->bank);
   delete e;
@@ -530,16 +561,19 @@ int pcb_reset(pcb_env_t* e, const uint8_t* d_reset_mask, void* stream) {
     e->slice = 0;
     e->step_no = 0;
     CU(cudaMemsetAsync(e->stats, 0, kStatSlots * 8 * sizeof(double), st));
-    if (e->job_count) CU(cudaMemsetAsync(e->job_count, 0, 2 * sizeof(uint32_t), st));
+    if (e->job_count) CU(cudaMemsetAsync(e->job_count, 0, 4 * sizeof(uint32_t), st));
   }
-  Params p = make_params(e);
+  Params p = make_params(e, true);
   p.reset_mask = d_reset_mask;
   p.reset_first = d_reset_mask ? 0 : 1;
   return launch(e, K_RESET, p, st);
 }
 
+// overlap = false: step kernel, then the reward kernel, both on `stream`.
+// overlap = true (pcb_rollout_random): the reward kernel of step t runs on the side
+// stream while the step kernel of step t+1 runs on `stream`; step t+2 waits for it.
 static int step_impl(pcb_env_t* e, const int32_t* d_actions, int action_format, uint64_t seed,
-                     int32_t* d_next_actions, void* stream) {
+                     int32_t* d_next_actions, void* stream, bool overlap) {
   int rc = ready(e);
   if (rc) return rc;
   if (!d_actions) return fail(PCB_ERR_INVALID, "d_actions is NULL");
@@ -547,6 +581,13 @@ static int step_impl(pcb_env_t* e, const int32_t* d_actions, int action_format, 
     return fail(PCB_ERR_INVALID, "unknown action format %d", action_format);
   CU(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream;
+  const bool routes = e->d.kind >= 2;
+  const int par = (int)(e->step_no & 1);
+  // the reward kernel of step t-2 used the same job buffer / scalar half
+  if (routes && overlap && e->step_no >= 2 && e->rew_pending[par]) {
+    CU(cudaStreamWaitEvent(st, e->ev_rew[par], 0));
+    e->rew_pending[par] = false;
+  }
   e->slice = (e->slice + 1) % e->ring;
   Params p = make_params(e);
   p.actions = d_actions;
@@ -555,13 +596,34 @@ static int step_impl(pcb_env_t* e, const int32_t* d_actions, int action_format, 
   p.actions_out = d_next_actions;
   rc = launch(e, K_STEP, p, st);
   if (rc) return rc;
-  if (e->d.kind >= 2) rc = launch(e, K_TERM, p, st);  // routing rewards of the episodes that ended
+  if (routes) {
+    if (!overlap) {
+      rc = launch(e, K_TERM, p, st);
+    } else {
+      CU(cudaEventRecord(e->ev_step[par], st));
+      CU(cudaStreamWaitEvent(e->side, e->ev_step[par], 0));
+      rc = launch(e, K_TERM, p, e->side, e->reward_grid_side);
+      if (rc) return rc;
+      CU(cudaEventRecord(e->ev_rew[par], e->side));
+      e->rew_pending[par] = true;
+    }
+  }
   e->step_no += 1;
   return rc;
 }
 
+// joins the overlapped reward kernels into `stream`
+static int join_rewards(pcb_env_t* e, cudaStream_t st) {
+  for (int i = 0; i < 2; ++i)
+    if (e->rew_pending[i]) {
+      CU(cudaStreamWaitEvent(st, e->ev_rew[i], 0));
+      e->rew_pending[i] = false;
+    }
+  return 0;
+}
+
 int pcb_step(pcb_env_t* e, const int32_t* d_actions, int action_format, void* stream) {
-  return step_impl(e, d_actions, action_format, 0, nullptr, stream);
+  return step_impl(e, d_actions, action_format, 0, nullptr, stream, false);
 }
 
 int pcb_sample_random_actions(pcb_env_t* e, uint64_t seed, int32_t* d_actions, void* stream) {
@@ -586,8 +648,9 @@ int pcb_step_host(pcb_env_t* e, const int32_t* h_actions, int action_format, dou
   CU(cudaMemcpyAsync(e->d_actions, h_actions, (size_t)e->n_envs * per * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   rc = pcb_step(e, e->d_actions, action_format, stream);
   if (rc) return rc;
-  CU(cudaMemcpyAsync(h_reward, e->base.reward, (size_t)e->n_envs * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(h_done, e->base.done, (size_t)e->n_envs, cudaMemcpyDeviceToHost, st));
+  const size_t half = (size_t)((e->step_no + 1) & 1) * e->n_envs;  // the half the step just wrote
+  CU(cudaMemcpyAsync(h_reward, e->base.reward + half, (size_t)e->n_envs * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(h_done, e->base.done + half, (size_t)e->n_envs, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   return 0;
 }
@@ -616,6 +679,10 @@ int pcb_get_tensor(pcb_env_t* e, const char* key, DLManagedTensor** out) {
 }
 
 int pcb_current_slice(pcb_env_t* e) { return e ? e->slice : fail(PCB_ERR_INVALID, "env is NULL"); }
+
+int pcb_current_result_half(pcb_env_t* e) {
+  return e ? (int)((e->step_no + 1) & 1) : fail(PCB_ERR_INVALID, "env is NULL");
+}
 
 int pcb_episode_stats(pcb_env_t* e, double out[8], int reset_counters, void* stream) {
   if (!e || !out) return fail(PCB_ERR_INVALID, "NULL argument");
@@ -654,6 +721,9 @@ int pcb_get_occupancy(pcb_env_t* e, uint64_t* h_rows, void* stream) {
 
 int64_t pcb_launch_count(pcb_env_t* e) { return e ? e->launches : 0; }
 
+#ifndef PCB_OVERLAP_REWARD
+#define PCB_OVERLAP_REWARD 1
+#endif
 int pcb_rollout_random(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_actions_log, void* stream) {
   int rc = ready(e);
   if (rc) return rc;
@@ -670,11 +740,11 @@ int pcb_rollout_random(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_acti
     if (t + 1 < n_steps)
       nxt = d_actions_log ? d_actions_log + (size_t)(t + 1) * per
                           : (cur == e->d_actions ? e->d_actions2 : e->d_actions);
-    rc = step_impl(e, cur, PCB_ACTION_TUPLE, seed, nxt, stream);
+    rc = step_impl(e, cur, PCB_ACTION_TUPLE, seed, nxt, stream, PCB_OVERLAP_REWARD != 0);
     if (rc) return rc;
     cur = nxt;
   }
-  return 0;
+  return join_rewards(e, (cudaStream_t)stream);
 }
 
 int pcb_enable_kernel_timing(pcb_env_t* e, int on) {

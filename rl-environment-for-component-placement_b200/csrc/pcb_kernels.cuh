@@ -846,14 +846,19 @@ __device__ __forceinline__ void centroid_route(const Dims& d, const RouteScratch
   }
   __syncwarp();
   crossings = count_crossings(rs, lane, n_pins);
-  // find_wirelength (pin:741-759): the reference's sequential float64 sum, net by net
+  // find_wirelength (pin:741-759): the reference's sequential float64 sum, net by net.
+  // Every lane runs the same chain; the operands come from registers via shuffles so
+  // only the additions are dependent.
   double acc = 0.0;
-  if (lane == 0)
-    for (int q = 0; q < n_pins; ++q) {
-      double v = rs.dist[q];
+  for (int q0 = 0; q0 < n_pins; q0 += 32) {
+    const double mine = q0 + lane < n_pins ? rs.dist[q0 + lane] : -1.0;
+    const int m = n_pins - q0 < 32 ? n_pins - q0 : 32;
+    for (int q = 0; q < m; ++q) {
+      const double v = __shfl_sync(kFull, mine, q);
       if (v >= 0.0) acc += v;
     }
-  wl = __shfl_sync(kFull, acc, 0);
+  }
+  wl = acc;
   __syncwarp();
 }
 
@@ -877,7 +882,7 @@ __device__ __forceinline__ void finish_episode(const S& sh, const Params& p, Env
     // all components placed: find_reward needs the routes -> leave the pin positions
     const int n_pins = e.hdr->n_pins;
     uint32_t idx = 0;
-    if (lane == 0) idx = atomicAdd(p.job_count + (p.step_no & 1), 1u);
+    if (lane == 0) idx = atomicAdd(p.job_count + (p.step_no & 3), 1u);
     idx = __shfl_sync(kFull, idx, 0);
     uint8_t* job = p.jobs + (size_t)idx * job_stride(sh.max_pins());
     if (lane == 0) {
@@ -1063,14 +1068,19 @@ step_kernel(const Params p) {
 // step with every component placed.  A small persistent grid walks the job list that
 // step_kernel left; one warp per job.  BEAM = true adds the beam-search router
 // (reward types "beam" / "both"), which needs far more registers.
+#ifndef PCB_REWARD_MIN_BLOCKS
+#define PCB_REWARD_MIN_BLOCKS 1
+#endif
 template <bool BEAM>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) reward_kernel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, PCB_REWARD_MIN_BLOCKS)
+reward_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const Dims& d = p.d;
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const int gw = blockIdx.x * kWarpsPerCta + wic, nw = gridDim.x * kWarpsPerCta;
-  const uint32_t count = p.job_count[p.step_no & 1];
-  if (gw == 0 && lane == 0) p.job_count[(p.step_no & 1) ^ 1] = 0;  // ready for the next step
+  const uint32_t count = p.job_count[p.step_no & 3];
+  // counters form a ring of 4: step t+2 cannot start before this kernel has finished
+  if (gw == 0 && lane == 0) p.job_count[(p.step_no + 2) & 3] = 0;
   const int scr_bytes = route_scratch_bytes(d.max_pins, d.K);
   RouteScratch rs = route_scratch(smem + (size_t)wic * ((scr_bytes + 15) & ~15), d.max_pins, d.K);
   for (uint32_t j = gw; j < count; j += nw) {

@@ -178,7 +178,7 @@ struct Params {
   const uint8_t* reset_mask;
   int reset_first;
   uint8_t* jobs;        // [N][job_stride] routing jobs of the current step
-  uint32_t* job_count;  // [2] job counters, indexed by step parity
+  uint32_t* job_count;  // [4] job counters, ring indexed by step number
   double* stats;      // [kStatSlots][8]
   uint64_t seed;
   uint64_t step_no;

@@ -129,9 +129,14 @@ class PcbVecEnv:
         self._last_actions = a  # keep alive until the kernels ran
         _lib.check(self.lib.pcb_step(self._h, ctypes.c_void_p(a.data_ptr()), fmt, self._stream()))
 
+    def results(self):
+        """reward, done and the info tensors of the step that just ran ([N] views)."""
+        h = self.lib.pcb_current_result_half(self._h)
+        return {k: v[h] for k, v in self._res.items()}
+
     def step(self, actions):
         self.step_async(actions)
-        r = self._res
+        r = self.results()
         info = {k: r[k] for k in ("wirelength", "num_intersections", "episode_return",
                                   "episode_length")}
         return self._obs(), r["reward"], r["done"], info

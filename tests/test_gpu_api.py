@@ -67,7 +67,9 @@ def test_fused_rollout_equals_sample_then_step(name):
         tot += r
     torch.cuda.synchronize()
     sa, sb = a.episode_stats(), b.episode_stats()
-    assert sa == sb and sa["episodes"] > 0
+    assert sa["episodes"] == sb["episodes"] > 0 and sa["sum_length"] == sb["sum_length"]
+    for k in sa:  # float64 atomics: the accumulation order differs between runs
+        assert np.isclose(sa[k], sb[k], rtol=1e-12, atol=0), k
     assert np.array_equal(a.occupancy(), b.occupancy())
     for k in a._obs():
         assert torch.equal(a._obs()[k], b._obs()[k]), k
