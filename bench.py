@@ -253,6 +253,9 @@ def gpu_arm(args, rank, world, local_rank):
     value = total_steps / (ms_max * 1e-3)
     e2e_value = total_steps / (e2e_ms_max * 1e-3)
 
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     peak, peak_src = load_peaks()
