@@ -43,8 +43,6 @@ int fail(int code, const char* fmt, ...) {
                   __FILE__, __LINE__);                                                  \
   } while (0)
 
-inline int align16(int v) { return (v + 15) & ~15; }
-
 struct TensorDesc {
   const char* key;
   void** ptr;
@@ -332,6 +330,8 @@ int pack_and_upload(pcb_env* e, const pcb_instance_bank_t* b) {
       prev_net = r.net;
       int max_row = d.kind == 3 ? d.C * d.L.P : d.L.P;
       if (r.pin_id >= max_row) return fail(PCB_ERR_INVALID, "instance %zu pin %d: pin_id %d >= %d", i, q, r.pin_id, max_row);
+      if (rank[r.comp] >= d.L.P)
+        return fail(PCB_ERR_INVALID, "instance %zu: component %d has more than %d pins", i, r.comp, d.L.P);
       r.rank = (uint8_t)rank[r.comp]++;
       // last writer of a (component, pin_id) feature row wins (update_all_pins_feature,
       // dummy_env_rectangular_pin.py:1521-1542); the spatial rows are keyed by pin_id alone
