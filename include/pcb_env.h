@@ -125,6 +125,15 @@ int pcb_upload_instances(pcb_env_t* env, const pcb_instance_bank_t* host_bank);
  * min_num_pins_per_net, max_num_pins_per_net, net_distribution, pin_spread}. */
 int pcb_generate_instances(pcb_env_t* env, const int32_t gen[12], uint64_t seed, int64_t count);
 
+/* The same generator without a handle or a GPU: fills caller-owned host arrays laid out
+ * like pcb_instance_bank_t (pin arrays may be NULL for PCB_KIND_RECT).  For tests and
+ * for building banks offline. */
+int pcb_generate_host(int kind, int max_num_components, int max_pins, int max_num_nets,
+                      const int32_t gen[12], uint64_t seed, int64_t count, int32_t* n_comp,
+                      uint8_t* comp_h, uint8_t* comp_w, int32_t* n_pins, int32_t* n_nets,
+                      uint8_t* pin_comp, uint8_t* pin_rx, uint8_t* pin_ry, uint8_t* pin_net,
+                      uint16_t* pin_id);
+
 /* DummyPlacementEnv.reset() (square:74, rect:310, pin:1544, spatial:1487) for
  * every env (d_reset_mask == NULL: episode 0 of each env, statistics cleared)
  * or for the envs whose mask byte is non-zero (they advance to their next

@@ -8,7 +8,7 @@ There is no CPU implementation: importing works anywhere, but creating an
 environment needs libpcbgpu.so and a CUDA device and fails loudly otherwise.
 """
 from .config import EnvSpec, make_spec, KINDS  # noqa: F401
-from .instances import InstanceBank  # noqa: F401
+from .instances import InstanceBank, generate_bank  # noqa: F401
 from .vec_env import PcbVecEnv  # noqa: F401
 from .gym_compat import GymCompatEnv, create_env, init_env  # noqa: F401
 from .wrappers import (  # noqa: F401

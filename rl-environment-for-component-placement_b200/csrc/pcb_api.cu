@@ -546,6 +546,34 @@ int pcb_generate_instances(pcb_env_t* e, const int32_t gen[12], uint64_t seed, i
   return pack_and_upload(e, &b);
 }
 
+int pcb_generate_host(int kind, int max_num_components, int max_pins, int max_num_nets,
+                      const int32_t gen[12], uint64_t seed, int64_t count, int32_t* n_comp,
+                      uint8_t* comp_h, uint8_t* comp_w, int32_t* n_pins, int32_t* n_nets,
+                      uint8_t* pin_comp, uint8_t* pin_rx, uint8_t* pin_ry, uint8_t* pin_net,
+                      uint16_t* pin_id) {
+  if (!gen || !n_comp || !comp_h || !comp_w) return fail(PCB_ERR_INVALID, "NULL argument");
+  if (kind < 1 || kind > 3 || count < 1) return fail(PCB_ERR_INVALID, "bad kind or count");
+  GenBank gb;
+  std::string why;
+  if (!generate_bank(gen, kind, max_num_components, max_pins, max_num_nets, seed, count, gb, why))
+    return fail(PCB_ERR_INVALID, "instance generator: %s", why.c_str());
+  memcpy(n_comp, gb.n_comp.data(), gb.n_comp.size() * sizeof(int32_t));
+  memcpy(comp_h, gb.comp_h.data(), gb.comp_h.size());
+  memcpy(comp_w, gb.comp_w.data(), gb.comp_w.size());
+  if (kind >= 2) {
+    if (!n_pins || !n_nets || !pin_comp || !pin_rx || !pin_ry || !pin_net || !pin_id)
+      return fail(PCB_ERR_INVALID, "NULL pin array");
+    memcpy(n_pins, gb.n_pins.data(), gb.n_pins.size() * sizeof(int32_t));
+    memcpy(n_nets, gb.n_nets.data(), gb.n_nets.size() * sizeof(int32_t));
+    memcpy(pin_comp, gb.pin_comp.data(), gb.pin_comp.size());
+    memcpy(pin_rx, gb.pin_rx.data(), gb.pin_rx.size());
+    memcpy(pin_ry, gb.pin_ry.data(), gb.pin_ry.size());
+    memcpy(pin_net, gb.pin_net.data(), gb.pin_net.size());
+    memcpy(pin_id, gb.pin_id.data(), gb.pin_id.size() * sizeof(uint16_t));
+  }
+  return 0;
+}
+
 static int ready(pcb_env_t* e) {
   if (!e) return fail(PCB_ERR_INVALID, "env is NULL");
   if (e->d.kind != 0 && !e->bank) return fail(PCB_ERR_STATE, "no instances uploaded (pcb_upload_instances / pcb_generate_instances)");

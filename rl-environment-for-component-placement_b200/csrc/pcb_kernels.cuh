@@ -263,13 +263,36 @@ struct BoardPath<FixedShape<KIND, HH, WW, CC, MH, MW, KK, MP>> {
 #endif
 constexpr int kLutBytes = PCB_OPT_LUT ? 256 * 8 : 0;  // CTA-wide byte-expansion table
 
-// 8 bits -> 8 bytes of 0/1, one shared-memory load (table built once per CTA)
-__device__ __forceinline__ void build_expand_lut(uint8_t* smem) {
+// 8 bits -> 8 bytes of 0/1 with one shared-memory load.  The 2 KB table lives in global
+// memory (static initialiser below, L2-resident) and every CTA copies it with one
+// 16-byte load + store per thread.
+#define PCB_S4(n) (((n) & 1u) | (((n) & 2u) << 7) | (((n) & 4u) << 14) | (((n) & 8u) << 21))
+#define PCB_E1(n) {PCB_S4((n) & 15u), PCB_S4((n) >> 4)}
+#define PCB_E4(n) PCB_E1(n), PCB_E1((n) + 1), PCB_E1((n) + 2), PCB_E1((n) + 3)
+#define PCB_E16(n) PCB_E4(n), PCB_E4((n) + 4), PCB_E4((n) + 8), PCB_E4((n) + 12)
+#define PCB_E64(n) PCB_E16(n), PCB_E16((n) + 16), PCB_E16((n) + 32), PCB_E16((n) + 48)
+__device__ const uint2 g_expand_lut[256] = {PCB_E64(0u), PCB_E64(64u), PCB_E64(128u), PCB_E64(192u)};
+
+// phase 1 (before the CTA's other global loads are consumed): fetch; phase 2: store + barrier
+__device__ __forceinline__ uint4 expand_lut_fetch() {
 #if PCB_OPT_LUT
-  uint2* lut = reinterpret_cast<uint2*>(smem);
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = make_uint2(spread4(i & 15), spread4(i >> 4));
+  if (threadIdx.x < 128) return reinterpret_cast<const uint4*>(g_expand_lut)[threadIdx.x];
+#endif
+  return make_uint4(0, 0, 0, 0);
+}
+__device__ __forceinline__ void expand_lut_store(uint8_t* smem, uint4 v) {
+#if PCB_OPT_LUT
+  if (blockDim.x >= 128) {
+    if (threadIdx.x < 128) reinterpret_cast<uint4*>(smem)[threadIdx.x] = v;
+  } else {  // small CTAs: every thread copies several chunks
+    for (int i = threadIdx.x; i < 128; i += blockDim.x)
+      reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(g_expand_lut)[i];
+  }
   __syncthreads();
 #endif
+}
+__device__ __forceinline__ void build_expand_lut(uint8_t* smem) {
+  expand_lut_store(smem, expand_lut_fetch());
 }
 
 __device__ __forceinline__ uint4 expand16(const uint2* lut, uint32_t b) {
@@ -946,25 +969,34 @@ step_kernel(const Params p) {
   const S sh(d);
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
   const int env = blockIdx.x * kWarpsPerCta + wic;
-  build_expand_lut(smem);
-  if (env >= p.n_envs) return;
+  const bool live = env < p.n_envs;
+  // issue every global load of this warp before anything waits: table, state, action
+  const uint4 lut_part = expand_lut_fetch();
+  const uint8_t* gstate_c = p.state + (size_t)(live ? env : 0) * sh.st_stride();
+  const int n16 = sh.st_stride() >> 4;
+  uint4 st0 = make_uint4(0, 0, 0, 0);
+  if (lane < n16) st0 = reinterpret_cast<const uint4*>(gstate_c)[lane];
+  const int kind = sh.kind();
+  int o = 0, x = 0, y = 0;
+  if (live) {  // FlatteningActionWrapper*: env_wrappers.py:80-98, wrapper_square.py:54-69
+    if (p.action_format == 1) {
+      int a = p.actions[env];
+      int hw = sh.H() * sh.W();
+      if (a < 0) { o = -1; }
+      else { o = a / hw; int rem = a - o * hw; x = rem / sh.W(); y = rem - x * sh.W(); }
+    } else if (kind == 0) {
+      x = p.actions[2 * env]; y = p.actions[2 * env + 1];
+    } else {
+      o = p.actions[3 * env]; x = p.actions[3 * env + 1]; y = p.actions[3 * env + 2];
+    }
+  }
+  expand_lut_store(smem, lut_part);
+  if (!live) return;
   Env<T> e(smem + kLutBytes + (size_t)wic * sh.sm_stride(), sh);
   uint8_t* gstate = p.state + (size_t)env * sh.st_stride();
-  copy16(e.sm, gstate, sh.st_stride(), lane);
-
-  // decode the action (FlatteningActionWrapper*: env_wrappers.py:80-98, wrapper_square.py:54-69)
-  const int kind = sh.kind();
-  int o = 0, x, y;
-  if (p.action_format == 1) {
-    int a = p.actions[env];
-    int hw = sh.H() * sh.W();
-    if (a < 0) { o = -1; x = y = 0; }
-    else { o = a / hw; int rem = a - o * hw; x = rem / sh.W(); y = rem - x * sh.W(); }
-  } else if (kind == 0) {
-    x = p.actions[2 * env]; y = p.actions[2 * env + 1];
-  } else {
-    o = p.actions[3 * env]; x = p.actions[3 * env + 1]; y = p.actions[3 * env + 2];
-  }
+  if (lane < n16) reinterpret_cast<uint4*>(e.sm)[lane] = st0;
+  for (int i = 32 + lane; i < n16; i += 32)
+    reinterpret_cast<uint4*>(e.sm)[i] = reinterpret_cast<const uint4*>(gstate)[i];
   __syncwarp();
 
   T occ[RPL];

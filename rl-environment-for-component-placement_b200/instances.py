@@ -62,3 +62,22 @@ class InstanceBank:
             setattr(self, name, arr)
             setattr(b, name, arr.ctypes.data_as(ctypes.c_void_p))
         return b
+
+
+def generate_bank(spec, count, seed=0):
+    """``count`` instances from the library's host generator (pcb_generate_host) as an
+    InstanceBank -- no GPU needed."""
+    from . import _lib
+
+    lib = _lib.load()
+    bank = InstanceBank(spec, count)
+    arr = (ctypes.c_int32 * 12)(*spec.generator_ranges())
+    ptr = lambda a: ctypes.c_void_p(a.ctypes.data)  # noqa: E731
+    from .config import KINDS
+
+    _lib.check(lib.pcb_generate_host(
+        KINDS[spec.kind], spec.max_num_components, max(spec.max_pins, 1), spec.max_num_nets, arr,
+        ctypes.c_uint64(seed), ctypes.c_int64(count), ptr(bank.n_comp), ptr(bank.comp_h),
+        ptr(bank.comp_w), ptr(bank.n_pins), ptr(bank.n_nets), ptr(bank.pin_comp), ptr(bank.pin_rx),
+        ptr(bank.pin_ry), ptr(bank.pin_net), ptr(bank.pin_id)))
+    return bank

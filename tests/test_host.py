@@ -175,3 +175,53 @@ def test_generators_follow_the_reference_rules():
             assert 0 <= x < it.comp_h[c] and 0 <= y < it.comp_w[c]
             assert (c, x, y) not in cells
             cells.add((c, x, y))
+
+
+def test_library_generator_matches_reference_distribution(pcbgpu):
+    """pcb_generate_host follows the reference's generate_instances construction with a
+    different RNG: the instances must satisfy the same invariants and have the same
+    distributions as the oracle generator (two-sample KS on the aggregate statistics)."""
+    from scipy import stats
+
+    for name in ("C", "S_pin", "S_spa"):
+        cfg = CONFIGS[name]
+        spatial = cfg["type"] == "rectangle_spatial_pin"
+        spec = pcbgpu.make_spec(cfg)
+        n = 1500
+        bank = pcbgpu.generate_bank(spec, n, seed=123)
+        np.random.seed(5)
+        random.seed(5)
+        ref = [oracle.generate_pin(cfg, spatial) for _ in range(n)]
+        lib_stats = {"n_comp": [], "n_pins": [], "n_nets": [], "area": [], "max_net": [], "max_comp": [],
+                     "comps_with_pins": []}
+        ref_stats = {k: [] for k in lib_stats}
+        for i in range(n):
+            nc, npn, nn = int(bank.n_comp[i]), int(bank.n_pins[i]), int(bank.n_nets[i])
+            h, w = bank.comp_h[i, :nc].astype(int), bank.comp_w[i, :nc].astype(int)
+            pc, pn = bank.pin_comp[i, :npn].astype(int), bank.pin_net[i, :npn].astype(int)
+            rx, ry = bank.pin_rx[i, :npn].astype(int), bank.pin_ry[i, :npn].astype(int)
+            assert cfg["min_num_components"] <= nc <= cfg["max_num_components"]
+            assert np.all(np.diff(pn) >= 0) and (npn == 0 or pn.max() == nn - 1)
+            per_net = np.bincount(pn, minlength=nn)
+            assert per_net.min() >= cfg["min_num_pins_per_net"]
+            assert per_net.max() <= cfg["max_num_pins_per_net"]
+            assert np.all(rx < h[pc]) and np.all(ry < w[pc])
+            assert len({(c, a, b) for c, a, b in zip(pc, rx, ry)}) == npn  # one pin per cell
+            per_comp = np.bincount(pc, minlength=nc)
+            assert np.all(per_comp <= h * w)
+            if spatial:
+                assert sorted(bank.pin_id[i, :npn].tolist()) == list(range(npn))
+            for dst, (a_nc, a_np, a_nn, a_area, a_pn, a_pc) in (
+                    (lib_stats, (nc, npn, nn, int((h * w).sum()), per_net, per_comp)),):
+                dst["n_comp"].append(a_nc); dst["n_pins"].append(a_np); dst["n_nets"].append(a_nn)
+                dst["area"].append(a_area); dst["max_net"].append(int(a_pn.max()))
+                dst["max_comp"].append(int(a_pc.max())); dst["comps_with_pins"].append(int((a_pc > 0).sum()))
+            it = ref[i]
+            pn2, pc2 = np.bincount(it.pin_net, minlength=it.n_nets), np.bincount(it.pin_comp, minlength=it.n_comp)
+            ref_stats["n_comp"].append(it.n_comp); ref_stats["n_pins"].append(it.n_pins)
+            ref_stats["n_nets"].append(it.n_nets); ref_stats["area"].append(int((it.comp_h * it.comp_w).sum()))
+            ref_stats["max_net"].append(int(pn2.max())); ref_stats["max_comp"].append(int(pc2.max()))
+            ref_stats["comps_with_pins"].append(int((pc2 > 0).sum()))
+        for k in lib_stats:
+            p = stats.ks_2samp(lib_stats[k], ref_stats[k]).pvalue
+            assert p > 1e-3, (name, k, p, np.mean(lib_stats[k]), np.mean(ref_stats[k]))
