@@ -125,6 +125,12 @@ int pcb_upload_instances(pcb_env_t* env, const pcb_instance_bank_t* host_bank);
  * min_num_pins_per_net, max_num_pins_per_net, net_distribution, pin_spread}. */
 int pcb_generate_instances(pcb_env_t* env, const int32_t gen[12], uint64_t seed, int64_t count);
 
+/* K8: the same generator as a kernel (one thread per instance) writing the device bank in
+ * place -- asynchronous on `stream`, no host round trip; call it between steps to keep
+ * feeding fresh instances (the bank is (re)allocated when `count` changes). */
+int pcb_generate_instances_device(pcb_env_t* env, const int32_t gen[12], uint64_t seed,
+                                  int64_t count, void* stream);
+
 /* The same generator without a handle or a GPU: fills caller-owned host arrays laid out
  * like pcb_instance_bank_t (pin arrays may be NULL for PCB_KIND_RECT).  For tests and
  * for building banks offline. */

@@ -12,7 +12,7 @@ SYMBOLS = (
     "pcb_step", "pcb_sample_random_actions", "pcb_step_host", "pcb_get_tensor",
     "pcb_current_slice", "pcb_episode_stats", "pcb_get_occupancy", "pcb_launch_count",
     "pcb_last_error", "pcb_abi_version", "pcb_rollout_random", "pcb_enable_kernel_timing",
-    "pcb_kernel_times", "pcb_current_result_half", "pcb_generate_host",
+    "pcb_kernel_times", "pcb_current_result_half", "pcb_generate_host", "pcb_generate_instances_device",
 )
 
 
@@ -64,6 +64,7 @@ def load():
     lib.pcb_destroy.argtypes = [vp]
     lib.pcb_upload_instances.argtypes = [vp, ctypes.POINTER(PcbInstanceBank)]
     lib.pcb_generate_instances.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), u64, i64]
+    lib.pcb_generate_instances_device.argtypes = [vp, ctypes.POINTER(ctypes.c_int32), u64, i64, vp]
     lib.pcb_reset.argtypes = [vp, vp, vp]
     lib.pcb_step.argtypes = [vp, vp, i32, vp]
     lib.pcb_sample_random_actions.argtypes = [vp, u64, vp, vp]

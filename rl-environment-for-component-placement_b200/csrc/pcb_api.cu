@@ -17,6 +17,7 @@
 
 #include "../../include/pcb_env.h"
 #include "pcb_gen.h"
+#include "pcb_gen_device.cuh"
 #include "pcb_kernels.cuh"
 
 using namespace pcb;
@@ -544,6 +545,40 @@ int pcb_generate_instances(pcb_env_t* e, const int32_t gen[12], uint64_t seed, i
     b.pin_net = gb.pin_net.data(); b.pin_id = gb.pin_id.data();
   }
   return pack_and_upload(e, &b);
+}
+
+int pcb_generate_instances_device(pcb_env_t* e, const int32_t gen[12], uint64_t seed, int64_t count,
+                                  void* stream) {
+  if (!e || !gen) return fail(PCB_ERR_INVALID, "NULL argument");
+  if (e->d.kind == 0) return fail(PCB_ERR_INVALID, "the square env has no instances");
+  if (count < 1 || count > 0x7fffffffLL) return fail(PCB_ERR_INVALID, "count out of range");
+  CU(cudaSetDevice(e->device));
+  {  // validate the ranges with the host generator (one throw-away instance)
+    GenBank gb;
+    std::string why;
+    if (!generate_bank(gen, e->d.kind, e->d.C, e->d.max_pins, e->d.K - 1, seed, 1, gb, why))
+      return fail(PCB_ERR_INVALID, "instance generator: %s", why.c_str());
+  }
+  const size_t bytes = (size_t)count * e->d.L.rec_stride;
+  if (!e->bank || e->bank_count != (uint32_t)count) {
+    CU(cudaStreamSynchronize((cudaStream_t)stream));  // nobody may still read the old bank
+    if (e->bank) { cudaFree(e->bank); e->bank = nullptr; }
+    void* p = nullptr;
+    CU(cudaMalloc(&p, bytes));
+    e->bank = reinterpret_cast<uint8_t*>(p);
+    e->bank_count = (uint32_t)count;
+  }
+  GenParams g;
+  g.kind = e->d.kind; g.C = e->d.C; g.P = e->d.L.P; g.max_pins = e->d.max_pins; g.K = e->d.K;
+  g.rec_stride = e->d.L.rec_stride; g.rec_comps = e->d.L.rec_comps; g.rec_pins = e->d.L.rec_pins;
+  g.min_w = gen[0]; g.max_w = gen[1]; g.min_h = gen[2]; g.max_h = gen[3]; g.min_c = gen[4];
+  g.max_c = gen[5]; g.min_nets = gen[6]; g.max_nets = gen[7]; g.lo = gen[8]; g.hi = gen[9];
+  g.nd = std::max(0, std::min(9, gen[10])); g.ps = std::max(0, std::min(9, gen[11]));
+  g.seed = seed; g.count = (uint32_t)count; g.bank = e->bank;
+  generate_kernel<<<(unsigned)((count + 127) / 128), 128, 0, (cudaStream_t)stream>>>(g);
+  CU(cudaGetLastError());
+  e->launches += 1;
+  return 0;
 }
 
 int pcb_generate_host(int kind, int max_num_components, int max_pins, int max_num_nets,

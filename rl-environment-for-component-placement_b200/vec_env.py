@@ -93,10 +93,17 @@ class PcbVecEnv:
         _lib.check(self.lib.pcb_upload_instances(self._h, ctypes.byref(s)))
         self.bank_size = bank.count
 
-    def generate_instances(self, count, seed=0):
+    def generate_instances(self, count, seed=0, on_device=False):
+        """Fill the bank with `count` generated instances: on the host (C++, uploaded) or
+        with the device generator kernel (asynchronous, in place -- call it between steps
+        to keep the environments on fresh instances)."""
         arr = (ctypes.c_int32 * 12)(*self.spec.generator_ranges())
-        _lib.check(self.lib.pcb_generate_instances(self._h, arr, ctypes.c_uint64(seed),
-                                                   ctypes.c_int64(count)))
+        if on_device:
+            _lib.check(self.lib.pcb_generate_instances_device(
+                self._h, arr, ctypes.c_uint64(seed), ctypes.c_int64(count), self._stream()))
+        else:
+            _lib.check(self.lib.pcb_generate_instances(self._h, arr, ctypes.c_uint64(seed),
+                                                       ctypes.c_int64(count)))
         self.bank_size = int(count)
 
     # -- gym surface ---------------------------------------------------------
