@@ -17,6 +17,7 @@ from .wrappers import (  # noqa: F401
     FlatteningActionMaskObservationWrapperSquare, FlatteningActionWrapperSquare)
 from .rollout import (RolloutCollector, allreduce_episode_stats, allreduce_stats,  # noqa: F401
                       shard_range)
+from .rllib_adapter import VectorEnvAdapter  # noqa: F401
 from . import _lib  # noqa: F401
 
 __all__ = ["PcbVecEnv", "GymCompatEnv", "create_env", "init_env", "InstanceBank", "EnvSpec",

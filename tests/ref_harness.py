@@ -57,6 +57,18 @@ CONFIGS = {
                         min_num_pins_per_net=2, reward_type="centroid", reward_beam_width=2,
                         weight_wirelength=0.5, weight_num_intersections=0.5),
 }
+CONFIGS["S_wide_pin"] = dict(  # 64-bit rows, runtime-shaped kernels, non-square grid
+    type="rectangle_pin", height=40, width=50, net_distribution=3, pin_spread=6,
+    min_component_w=2, max_component_w=6, min_component_h=1, max_component_h=5,
+    max_num_components=12, min_num_components=5, min_num_nets=2, max_num_nets=7,
+    max_num_pins_per_net=7, min_num_pins_per_net=2, reward_type="both", reward_beam_width=3,
+    weight_wirelength=0.3, weight_num_intersections=0.9)
+CONFIGS["S_wide_spa"] = dict(CONFIGS["S_wide_pin"], type="rectangle_spatial_pin", height=64, width=33,
+                             reward_type="centroid", reward_beam_width=2)
+CONFIGS["S_wide_sq"] = dict(type="square", height=64, width=64, component_n=5)
+CONFIGS["S_wide_rect"] = dict(type="rectangle", height=33, width=64, min_component_w=3,
+                              max_component_w=9, min_component_h=2, max_component_h=8,
+                              max_num_components=14, min_num_components=8)
 CONFIGS["C_both"] = dict(CONFIGS["C"], reward_type="both")
 CONFIGS["C_beam"] = dict(CONFIGS["C"], reward_type="beam")
 CONFIGS["D"] = dict(CONFIGS["C"], type="rectangle_spatial_pin")

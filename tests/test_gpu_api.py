@@ -188,3 +188,21 @@ def test_ppo_collector_end_to_end(name):
     adv, _ = compute_gae(r, v, d, torch.zeros(1), gamma=1.0, lam=1.0)
     assert adv[:, 0].tolist() == [2.0, 1.0, 1.0]
     env.close()
+
+
+def test_vector_env_adapter_surface():
+    """the RLlib VectorEnv method surface (duck-typed, ray is not installed)."""
+    import pcbgpu
+
+    ad = pcbgpu.VectorEnvAdapter(CONFIGS["REF_pin"], 6, seed=2)
+    obs = ad.vector_reset()
+    assert len(obs) == 6 and obs[0]["action_mask"].shape == (400,) and obs[0]["grid"].dtype == np.float64
+    rng = np.random.default_rng(0)
+    for t in range(5):
+        acts = [int(rng.choice(np.flatnonzero(o["action_mask"]))) for o in obs]
+        obs, rew, done, infos = ad.vector_step(acts)
+        assert len(rew) == 6 and all(isinstance(d, bool) for d in done)
+    assert all(done) and all(set(i) == {"wirelength", "num_intersections"} for i in infos)
+    o3 = ad.reset_at(3)
+    assert o3["grid"].sum() == 0 and obs[2]["grid"].sum() > 0
+    ad.close()

@@ -51,3 +51,14 @@ def test_large_grid_E():
 def test_autoreset(name):
     run_parity(name, range(32), autoreset=True, episodes=3)
     run_parity(name, range(32, 48), autoreset=True, episodes=3, p_invalid=0.1)
+
+
+@pytest.mark.parametrize("name", ["S_wide_pin", "S_wide_spa", "S_wide_rect", "S_wide_sq"])
+def test_wide_grids_runtime_shaped(name):
+    """64-bit bitboard rows with the runtime-shaped kernels (grids up to 64x64, non-square)."""
+    st = {}
+    n = 8 if name == "S_wide_sq" else 24
+    run_parity(name, range(n), extra_steps=2, stats=st)
+    run_parity(name, range(n, n + 12), p_invalid=0.1, stats=st)
+    run_parity(name, range(8), autoreset=True, episodes=2, stats=st)
+    assert st["reward_inexact"] == 0, st

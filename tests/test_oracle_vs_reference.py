@@ -85,3 +85,13 @@ def test_spatial(name):
 
 def test_large_E():
     run_pair("E", range(3))
+
+
+@pytest.mark.parametrize("name", ["S_wide_pin", "S_wide_spa", "S_wide_rect"])
+def test_wide_grids(name):
+    run_pair(name, range(12), extra_steps=2)
+    run_pair(name, range(12, 18), p_invalid=0.1)
+
+
+def test_wide_square():
+    run_pair("S_wide_sq", range(2))
