@@ -188,6 +188,16 @@ int pcb_episode_stats(pcb_env_t* env, double out[8], int reset_counters, void* s
  * 64-bit words, [N, 64]) to the host -- for tests and checkpointing. */
 int pcb_get_occupancy(pcb_env_t* env, uint64_t* h_rows, void* stream);
 
+/* Checkpoint / resume and inspection of the compact per-env state records
+ * (layout: csrc/pcb_layout.h).  out = {st_stride, off_components, off_pins, off_bitboard,
+ * max_num_components, max_pins, bytes per bitboard row word, rows stored}.  get/set copy
+ * [N, st_stride] bytes and the step counter (which seeds the device random policy);
+ * the instance bank is not part of the state -- restore it with the same upload /
+ * generator call.  Both synchronise `stream`. */
+int pcb_state_layout(pcb_env_t* env, int32_t out[8]);
+int pcb_get_state(pcb_env_t* env, void* h_state, uint64_t* step_no, void* stream);
+int pcb_set_state(pcb_env_t* env, const void* h_state, uint64_t step_no, void* stream);
+
 /* Number of kernels this handle has launched so far (bench: gpu_launches). */
 int64_t pcb_launch_count(pcb_env_t* env);
 

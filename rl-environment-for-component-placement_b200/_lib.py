@@ -12,7 +12,8 @@ SYMBOLS = (
     "pcb_step", "pcb_sample_random_actions", "pcb_step_host", "pcb_get_tensor",
     "pcb_current_slice", "pcb_episode_stats", "pcb_get_occupancy", "pcb_launch_count",
     "pcb_last_error", "pcb_abi_version", "pcb_rollout_random", "pcb_enable_kernel_timing",
-    "pcb_kernel_times", "pcb_current_result_half", "pcb_generate_host", "pcb_generate_instances_device",
+    "pcb_kernel_times", "pcb_current_result_half", "pcb_generate_host", "pcb_generate_instances_device", "pcb_state_layout", "pcb_get_state",
+    "pcb_set_state",
 )
 
 
@@ -72,6 +73,9 @@ def load():
     lib.pcb_get_tensor.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
     lib.pcb_current_slice.argtypes = [vp]
     lib.pcb_current_result_half.argtypes = [vp]
+    lib.pcb_state_layout.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]
+    lib.pcb_get_state.argtypes = [vp, vp, ctypes.POINTER(u64), vp]
+    lib.pcb_set_state.argtypes = [vp, vp, u64, vp]
     lib.pcb_generate_host.argtypes = [i32, i32, i32, i32, ctypes.POINTER(ctypes.c_int32), u64, i64] + [vp] * 10
     lib.pcb_episode_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_double), i32, vp]
     lib.pcb_get_occupancy.argtypes = [vp, vp, vp]

@@ -782,6 +782,35 @@ int pcb_get_occupancy(pcb_env_t* e, uint64_t* h_rows, void* stream) {
   return 0;
 }
 
+int pcb_state_layout(pcb_env_t* e, int32_t out[8]) {
+  if (!e || !out) return fail(PCB_ERR_INVALID, "NULL argument");
+  const Dims& d = e->d;
+  out[0] = d.L.st_stride; out[1] = d.L.st_comps; out[2] = d.L.st_pins; out[3] = d.L.st_occ;
+  out[4] = d.C; out[5] = d.max_pins; out[6] = e->wide ? 8 : 4; out[7] = e->wide ? 64 : 32;
+  return 0;
+}
+
+int pcb_get_state(pcb_env_t* e, void* h_state, uint64_t* step_no, void* stream) {
+  if (!e || !h_state) return fail(PCB_ERR_INVALID, "NULL argument");
+  CU(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaMemcpyAsync(h_state, e->state, (size_t)e->n_envs * e->d.L.st_stride, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  if (step_no) *step_no = e->step_no;
+  return 0;
+}
+
+int pcb_set_state(pcb_env_t* e, const void* h_state, uint64_t step_no, void* stream) {
+  if (!e || !h_state) return fail(PCB_ERR_INVALID, "NULL argument");
+  CU(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  CU(cudaMemcpyAsync(e->state, h_state, (size_t)e->n_envs * e->d.L.st_stride, cudaMemcpyHostToDevice, st));
+  if (e->job_count) CU(cudaMemsetAsync(e->job_count, 0, 4 * sizeof(uint32_t), st));
+  CU(cudaStreamSynchronize(st));
+  e->step_no = step_no;
+  return 0;
+}
+
 int64_t pcb_launch_count(pcb_env_t* e) { return e ? e->launches : 0; }
 
 #ifndef PCB_OVERLAP_REWARD

@@ -132,7 +132,7 @@ class PPOTrainer:
                 self.opt.zero_grad(set_to_none=True)
                 loss.backward()
                 self.opt.step()
-                losses.append(float(loss))
+                losses.append(float(loss.detach()))
         return sum(losses) / len(losses)
 
     def train(self, iterations=1):

@@ -206,6 +206,54 @@ class PcbVecEnv:
                                               self._stream()))
         return rows
 
+    # -- checkpoint / inspection ---------------------------------------------
+    def state_layout(self):
+        out = (ctypes.c_int32 * 8)()
+        _lib.check(self.lib.pcb_state_layout(self._h, out))
+        keys = ("stride", "off_comps", "off_pins", "off_board", "max_comps", "max_pins",
+                "word_bytes", "rows")
+        return dict(zip(keys, list(out)))
+
+    def state_dict(self):
+        """The compact per-env state records + step counter (the env has no other mutable
+        state; the instance bank is an input and is not included)."""
+        lay = self.state_layout()
+        buf = np.zeros((self.num_envs, lay["stride"]), np.uint8)
+        step = ctypes.c_uint64()
+        _lib.check(self.lib.pcb_get_state(self._h, ctypes.c_void_p(buf.ctypes.data),
+                                          ctypes.byref(step), self._stream()))
+        return {"state": buf, "step_no": int(step.value), "kind": self.kind}
+
+    def load_state_dict(self, sd):
+        buf = np.ascontiguousarray(sd["state"], np.uint8)
+        if buf.shape != (self.num_envs, self.state_layout()["stride"]) or sd["kind"] != self.kind:
+            raise ValueError("state_dict does not match this environment")
+        _lib.check(self.lib.pcb_set_state(self._h, ctypes.c_void_p(buf.ctypes.data),
+                                          ctypes.c_uint64(sd["step_no"]), self._stream()))
+
+    def decode_state(self, sd=None):
+        """Per env: components (h, w, x, y; -1 = not placed) and pins (component,
+        relative_x/y after rotation, absolute_x/y, net, pin_id) parsed from the state
+        records -- what the reference keeps in env.components / env.pins."""
+        sd = sd or self.state_dict()
+        lay, raw = self.state_layout(), sd["state"]
+        hdr = raw[:, :16]
+        n_comp, n_pins, cur = hdr[:, 0], hdr[:, 2].astype(int) | (hdr[:, 3].astype(int) << 8), hdr[:, 4]
+        out = []
+        for i in range(self.num_envs):
+            c = raw[i, lay["off_comps"]:lay["off_comps"] + 4 * int(n_comp[i])].reshape(-1, 4).astype(int)
+            c[:, 2:][c[:, 2:] == 255] = -1
+            p = raw[i, lay["off_pins"]:lay["off_pins"] + 8 * int(n_pins[i])].reshape(-1, 8).astype(int)
+            pins = []
+            for q in p:
+                comp, rx, ry, net, pid = q[0], q[1], q[2], q[3], q[4] | (q[5] << 8)
+                x, y = c[comp, 2], c[comp, 3]
+                pins.append(dict(component_id=comp, relative_x=rx, relative_y=ry, net_id=net, pin_id=pid,
+                                 absolute_x=-1 if x < 0 else x + rx, absolute_y=-1 if x < 0 else y + ry))
+            out.append(dict(components=[dict(h=r[0], w=r[1], x=r[2], y=r[3]) for r in c],
+                            pins=pins, current=int(cur[i])))
+        return out
+
     def episode_stats(self, reset=False):
         out = (ctypes.c_double * 8)()
         _lib.check(self.lib.pcb_episode_stats(self._h, out, 1 if reset else 0, self._stream()))

@@ -206,3 +206,44 @@ def test_vector_env_adapter_surface():
     o3 = ad.reset_at(3)
     assert o3["grid"].sum() == 0 and obs[2]["grid"].sum() > 0
     ad.close()
+
+
+def test_checkpoint_resume_is_deterministic():
+    env = make("C_both", 256, seed=6)
+    env.reset()
+    env.rollout_random(7, seed=5)
+    sd = env.state_dict()
+
+    def run():
+        out = []
+        for t in range(15):
+            _, r, d, _ = env.step(env.sample_random_actions(seed=5))
+            out.append((r.clone(), d.clone()))
+        return out
+
+    a = run()
+    env.load_state_dict(sd)
+    b = run()
+    assert all(torch.equal(x[0], y[0]) and torch.equal(x[1], y[1]) for x, y in zip(a, b))
+    dec = env.decode_state()
+    assert len(dec) == 256 and all(len(e["components"]) == 10 for e in dec)
+    env.close()
+
+
+def test_export_in_reference_pickle_format(tmp_path):
+    import pickle
+
+    from pcbgpu.export import export_rollouts
+
+    comps, actions = export_rollouts(CONFIGS["REF_pin"], 5, str(tmp_path), seed=3)
+    assert len(comps) == 5 and all(len(a) == 5 and len(a[0]) == 3 for a in actions)
+    raw = open(tmp_path / "components.pkl", "rb").read()
+    assert b"environment.dummy_env_rectangular_pin" in raw and b"Component" in raw and b"Pin" in raw
+    acts = pickle.load(open(tmp_path / "actions.pkl", "rb"))
+    assert acts == actions
+    for ep_comps, ep_actions in zip(comps, actions):
+        for c, (o, x, y) in zip(ep_comps, ep_actions):
+            assert c.placed and c.position == (x, y)
+            ph, pw = (c.h, c.w) if o in (0, 2) else (c.w, c.h)
+            for pin in c.pins:  # pins lie inside the placed footprint
+                assert x <= pin.absolute_x < x + ph and y <= pin.absolute_y < y + pw
