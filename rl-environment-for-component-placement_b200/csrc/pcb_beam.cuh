@@ -223,8 +223,8 @@ __device__ __forceinline__ void beam_route(const Dims& d, const RouteScratch& rs
                                            int n_pins, int n_nets, int& crossings, double& wl) {
   for (int q = lane; q < n_pins; q += 32) {
     const int nx = rs.nxt[q];
-    double x2 = 0.0, y2 = 0.0, len = -1.0;
-    uint32_t box = kNoBox;
+    double x2 = 0.0, y2 = 0.0, len = 0.0;
+    uint2 box = no_box();
     if (nx != 0xFFFF) {
       const double x1 = (double)rs.px[q], y1 = (double)rs.py[q];
       x2 = (double)rs.px[nx]; y2 = (double)rs.py[nx];

@@ -429,10 +429,45 @@ __device__ __forceinline__ uint32_t action_rand(uint64_t seed, uint32_t env, uin
 #endif
 }
 
+#ifndef PCB_SAMPLE_TRIES
+#define PCB_SAMPLE_TRIES 6
+#endif
+// Uniform draw over the valid (orientation, row, column) triples.  Fast path: rejection
+// sampling -- a uniform cell of the O x H x W box is accepted when its mask bit is set
+// (exactly uniform over the valid cells; the masks are dense early in an episode, so one
+// or two tries suffice).  After PCB_SAMPLE_TRIES misses the exact method runs: k-th set
+// bit in np.argwhere order via a warp prefix sum.
 template <int RPL, typename T, typename S>
 __device__ __forceinline__ void sample_action(const S& sh, const T (&m0)[RPL], const T (&m1)[RPL],
                                               uint64_t seed, int env, uint64_t step_no, int lane,
                                               int32_t* out) {
+  {
+    T anyv = T(0);
+#pragma unroll
+    for (int k = 0; k < RPL; ++k) anyv |= m0[k] | m1[k];
+    if (__any_sync(kFull, anyv != T(0))) {
+      const int H = sh.H(), W = sh.W();
+      const uint32_t cells = (uint32_t)(sh.O() * H * W);
+      for (int t = 0; t < PCB_SAMPLE_TRIES; ++t) {
+        const uint32_t r = action_rand(seed + 0x632BE59BD9B4E019ull * (uint64_t)(t + 1), (uint32_t)env, step_no);
+        const int idx = (int)__umulhi(r, cells);
+        const int o = idx / (H * W), rem = idx - o * (H * W);
+        const int row = rem / W, col = rem - row * W;
+        T mine = T(0);
+#pragma unroll
+        for (int k = 0; k < RPL; ++k)
+          if ((row >> 5) == k) mine = (o & 1) ? m1[k] : m0[k];
+        const T bits = __shfl_sync(kFull, mine, row & 31);
+        if ((bits >> col) & T(1)) {  // warp-uniform
+          if (lane == 0) {
+            if (sh.kind() == 0) { out[2 * env] = row; out[2 * env + 1] = col; }
+            else { out[3 * env] = o; out[3 * env + 1] = row; out[3 * env + 2] = col; }
+          }
+          return;
+        }
+      }
+    }
+  }
   int c0 = 0, c1 = 0;
 #pragma unroll
   for (int k = 0; k < RPL; ++k) { c0 += popc_t<T>(m0[k]); c1 += popc_t<T>(m1[k]); }
@@ -737,15 +772,17 @@ __device__ __forceinline__ bool segments_cross(double x1, double y1, double x2, 
 
 // Per-warp scratch of the reward.  A route is stored per pin: the segment "headed" by
 // pin q runs from (px[q], py[q]) to (x2[q], y2[q]); box[q] is a conservative integer
-// bounding box (x0 | y0<<8 | x1<<16 | y1<<24), kNoBox when pin q heads no segment.
-constexpr uint32_t kNoBox = 0x0000ffffu;
+// bounding box as two words with 16-bit fields: lo = x0 | y0<<16 and hi = (x1 | y1<<16) |
+// kBoxGuard; kNoBoxLo in lo (and an empty hi) when pin q heads no segment.
+constexpr uint32_t kBoxGuard = 0x80008000u;
+constexpr uint32_t kNoBoxLo = 0x7fff7fffu;
 struct RouteScratch {
   double* x2;
   double* y2;
   double* dist;
   double* cx;         // [K] centroid per net
   double* cy;
-  uint32_t* box;
+  uint2* box;         // [max_pins] (lo, guarded hi)
   uint32_t* queue;    // [kPairQueue] candidate pairs (s << 16 | t)
   int16_t* px;
   int16_t* py;
@@ -763,7 +800,7 @@ __device__ __forceinline__ RouteScratch route_scratch(uint8_t* scr, int max_pins
   r.dist = reinterpret_cast<double*>(q); q += max_pins * 8;
   r.cx = reinterpret_cast<double*>(q); q += K * 8;
   r.cy = reinterpret_cast<double*>(q); q += K * 8;
-  r.box = reinterpret_cast<uint32_t*>(q); q += max_pins * 4;
+  r.box = reinterpret_cast<uint2*>(q); q += max_pins * 8;
   r.queue = reinterpret_cast<uint32_t*>(q); q += kPairQueue * 4;
   r.px = reinterpret_cast<int16_t*>(q); q += max_pins * 2;
   r.py = reinterpret_cast<int16_t*>(q); q += max_pins * 2;
@@ -774,16 +811,18 @@ __device__ __forceinline__ RouteScratch route_scratch(uint8_t* scr, int max_pins
   return r;
 }
 
-__device__ __forceinline__ uint32_t make_box(double xa, double ya, double xb, double yb) {
+__device__ __forceinline__ uint2 make_box(double xa, double ya, double xb, double yb) {
   int x0 = (int)floor(fmin(xa, xb)), x1 = (int)ceil(fmax(xa, xb));
   int y0 = (int)floor(fmin(ya, yb)), y1 = (int)ceil(fmax(ya, yb));
-  return (uint32_t)x0 | ((uint32_t)y0 << 8) | ((uint32_t)x1 << 16) | ((uint32_t)y1 << 24);
+  return make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16),
+                    ((uint32_t)x1 | ((uint32_t)y1 << 16)) | kBoxGuard);
 }
+__device__ __forceinline__ uint2 no_box() { return make_uint2(kNoBoxLo, kBoxGuard); }
 
-__device__ __forceinline__ bool boxes_touch(uint32_t a, uint32_t b) {
-  uint32_t lo = __vmaxu4(a, b) & 0xffffu;  // max of the two lower corners (bytes 0,1)
-  uint32_t hi = __vminu4(a, b) >> 16;      // min of the two upper corners
-  return __vcmpleu4(lo, hi) == 0xffffffffu;
+// closed boxes a, b touch  <=>  b.hi >= a.lo and a.hi >= b.lo in both fields; the guard bit
+// of a field survives the subtraction exactly when the difference is non-negative
+__device__ __forceinline__ bool boxes_touch(uint2 a, uint2 b) {
+  return (((b.y - a.x) & (a.y - b.x)) & kBoxGuard) == kBoxGuard;
 }
 
 // positions, net ranges, centroids (get_net_pin_positions pin:1266-1280, get_centroid :1282-1294)
@@ -821,16 +860,16 @@ __device__ __forceinline__ int count_crossings(const RouteScratch& rs, int lane,
   };
   for (int t0 = 0; t0 < n_pins; t0 += 32) {
     const int t = t0 + lane;
-    uint32_t mine = kNoBox;
+    uint2 mine = no_box();
     int my_hi = 0;
     if (t < n_pins) {
       mine = rs.box[t];
-      if (mine != kNoBox) my_hi = rs.net_off[rs.net[t]];  // segments of earlier nets only
+      if (mine.x != kNoBoxLo) my_hi = rs.net_off[rs.net[t]];  // segments of earlier nets only
     }
     const int smax = __reduce_max_sync(kFull, my_hi);
     for (int s = 0; s < smax; ++s) {
-      const uint32_t other = rs.box[s];
-      if (other == kNoBox) continue;  // warp-uniform
+      const uint2 other = rs.box[s];
+      if (other.x == kNoBoxLo) continue;  // warp-uniform
       const bool pass = s < my_hi && boxes_touch(mine, other);
       const unsigned b = __ballot_sync(kFull, pass);
       if (b == 0) continue;
@@ -856,8 +895,8 @@ __device__ __forceinline__ void centroid_route(const Dims& d, const RouteScratch
   for (int q = lane; q < n_pins; q += 32) {
     const int net = rs.net[q];
     const int lo = rs.net_off[net], cnt = rs.net_off[net + 1] - lo;
-    double x2 = 0.0, y2 = 0.0, len = -1.0;
-    uint32_t box = kNoBox;
+    double x2 = 0.0, y2 = 0.0, len = 0.0;  // + 0.0 leaves the running sum unchanged
+    uint2 box = no_box();
     if (cnt != 2 || q == lo) {
       if (cnt == 2) { x2 = (double)rs.px[q + 1]; y2 = (double)rs.py[q + 1]; }
       else { x2 = rs.cx[net]; y2 = rs.cy[net]; }
@@ -874,12 +913,9 @@ __device__ __forceinline__ void centroid_route(const Dims& d, const RouteScratch
   // only the additions are dependent.
   double acc = 0.0;
   for (int q0 = 0; q0 < n_pins; q0 += 32) {
-    const double mine = q0 + lane < n_pins ? rs.dist[q0 + lane] : -1.0;
+    const double mine = q0 + lane < n_pins ? rs.dist[q0 + lane] : 0.0;
     const int m = n_pins - q0 < 32 ? n_pins - q0 : 32;
-    for (int q = 0; q < m; ++q) {
-      const double v = __shfl_sync(kFull, mine, q);
-      if (v >= 0.0) acc += v;
-    }
+    for (int q = 0; q < m; ++q) acc += __shfl_sync(kFull, mine, q);
   }
   wl = acc;
   __syncwarp();

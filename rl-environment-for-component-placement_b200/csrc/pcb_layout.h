@@ -86,7 +86,7 @@ PCB_HD constexpr int maxc(int a, int b) { return a > b ? a : b; }
 
 // terminal-reward scratch per warp: per-pin arrays + per-net arrays + pair queue
 PCB_HD constexpr int route_scratch_bytes(int max_pins, int K) {
-  return max_pins * (8 + 8 + 8 + 4 + 2 + 2 + 2 + 1) + K * (8 + 8 + 2 + 2) + 2 + kPairQueue * 4 + 64;
+  return max_pins * (8 + 8 + 8 + 8 + 2 + 2 + 2 + 1) + K * (8 + 8 + 2 + 2) + 2 + kPairQueue * 4 + 64;
 }
 
 // fast_board: the kernel expands bitboards straight from registers (FixedShape 16/32/64
