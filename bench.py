@@ -225,9 +225,16 @@ def gpu_arm(args, rank, world, local_rank):
     # ---- pass 3: end to end through host buffers (e2e) ---------------------------
     import numpy as np
 
-    h_actions = torch.empty((K, N, width), dtype=torch.int32, pin_memory=True)
-    h_actions.copy_(log)
-    del log
+    # the reference's PPO loop sends flat Discrete actions (FlatteningActionWrapper*); the
+    # step kernel decodes them, so the host buffer holds one int32 per env
+    H_, W_ = env.spec.height, env.spec.width
+    if width == 3:
+        flat = (log[..., 0] * H_ + log[..., 1]) * W_ + log[..., 2]
+    else:
+        flat = log[..., 0] * W_ + log[..., 1]
+    h_actions = torch.empty((K, N), dtype=torch.int32, pin_memory=True)
+    h_actions.copy_(flat.int())
+    del log, flat
     h_reward = torch.empty((N,), dtype=torch.float64, pin_memory=True)
     h_done = torch.empty((N,), dtype=torch.uint8, pin_memory=True)
     a_np, r_np, d_np = h_actions.numpy(), h_reward.numpy(), h_done.numpy()
@@ -288,8 +295,8 @@ def gpu_arm(args, rank, world, local_rank):
             "timing": "CUDA events on the launching stream around %d steps, max over ranks" % K,
         },
         "e2e": {"value": e2e_value, "unit": "env-steps/s",
-                "h2d_bytes_per_step": int(N * width * 4), "d2h_bytes_per_step": int(N * 9),
-                "path": "pcb_step_host (C ABI): pinned host actions -> H2D -> step -> D2H reward+done, "
+                "h2d_bytes_per_step": int(N * 4), "d2h_bytes_per_step": int(N * 9),
+                "path": "pcb_step_host (C ABI): pinned host flat actions (int32 per env) -> H2D -> step -> D2H reward+done, "
                         "sync every step; observations stay on device (DLPack)"},
         "gpu_launches": int(launches),
         "clocks": clk,

@@ -127,6 +127,19 @@ __device__ __forceinline__ int nth_bit(T v, int n) {
   }
 }
 
+// Observation stores are streaming (st.global.cs, evict-first in L2): the slab is written
+// once and never re-read by these kernels, while the per-env state and the instance bank
+// ARE re-read every step and should stay L2-resident.  Measured on the bare store pattern
+// of config C: 85 us with default stores, 75 us with .cs (profiles/README.md).
+template <typename V>
+__device__ __forceinline__ void st_stream(V* p, V v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(uint8_t* p, uint8_t v) {
+  __stcs(reinterpret_cast<unsigned char*>(p), (unsigned char)v);
+}
+__device__ __forceinline__ void st_stream(uint32_t* p, uint32_t v) {
+  __stcs(reinterpret_cast<unsigned int*>(p), (unsigned int)v);
+}
+
 // smem -> global copy of one environment's slice of a tensor, widest store the
 // alignment allows (16 B when the per-env size is a multiple of 16).
 __device__ __forceinline__ void copy_out(void* dst, const void* src, int nbytes, int lane) {
@@ -134,15 +147,15 @@ __device__ __forceinline__ void copy_out(void* dst, const void* src, int nbytes,
   if ((a & 15) == 0) {
     const uint4* s = reinterpret_cast<const uint4*>(src);
     uint4* d = reinterpret_cast<uint4*>(dst);
-    for (int i = lane; i < (nbytes >> 4); i += 32) d[i] = s[i];
+    for (int i = lane; i < (nbytes >> 4); i += 32) st_stream(d + i, s[i]);
   } else if ((a & 3) == 0) {
     const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
     uint32_t* d = reinterpret_cast<uint32_t*>(dst);
-    for (int i = lane; i < (nbytes >> 2); i += 32) d[i] = s[i];
+    for (int i = lane; i < (nbytes >> 2); i += 32) st_stream(d + i, s[i]);
   } else {
     const uint8_t* s = reinterpret_cast<const uint8_t*>(src);
     uint8_t* d = reinterpret_cast<uint8_t*>(dst);
-    for (int i = lane; i < nbytes; i += 32) d[i] = s[i];
+    for (int i = lane; i < nbytes; i += 32) st_stream(d + i, s[i]);
   }
 }
 
@@ -317,14 +330,14 @@ __device__ __forceinline__ void write_board(const S& sh, uint8_t* dst, const T (
         for (int half = 0; half < 2; ++half) {
           uint32_t w = __shfl_sync(kFull, regs[0], (lane >> 1) + 16 * half);
           uint4 v = expand16(lut, w >> (16 * (lane & 1)));
-          d4[half * 32 + lane] = v;
-          if (dup_off) e4[half * 32 + lane] = v;
+          st_stream(d4 + half * 32 + lane, v);
+          if (dup_off) st_stream(e4 + half * 32 + lane, v);
         }
       } else {  // 16x16: one 16-byte chunk per row
         if (lane < 16) {
           uint4 v = expand16(lut, (uint32_t)regs[0]);
-          d4[lane] = v;
-          if (dup_off) e4[lane] = v;
+          st_stream(d4 + lane, v);
+          if (dup_off) st_stream(e4 + lane, v);
         }
       }
     } else {  // 64x64: 4 chunks per row, 256 chunks
@@ -332,8 +345,8 @@ __device__ __forceinline__ void write_board(const S& sh, uint8_t* dst, const T (
       for (int i = 0; i < 8; ++i) {
         T w = __shfl_sync(kFull, regs[i >> 2], (i & 3) * 8 + (lane >> 2));
         uint4 v = expand16(lut, (uint32_t)(w >> (16 * (lane & 3))));
-        d4[i * 32 + lane] = v;
-        if (dup_off) e4[i * 32 + lane] = v;
+        st_stream(d4 + i * 32 + lane, v);
+        if (dup_off) st_stream(e4 + i * 32 + lane, v);
       }
     }
   } else {
@@ -348,16 +361,16 @@ __device__ __forceinline__ void write_board(const S& sh, uint8_t* dst, const T (
         else if (cpr == 1) { row = q; part = 0; }
         else { row = q / 3; part = q - 3 * row; }
         uint4 v = spread16((uint32_t)(rows[row] >> (16 * part)) & 0xffffu);
-        d4[q] = v;
-        if (dup_off) e4[q] = v;
+        st_stream(d4 + q, v);
+        if (dup_off) st_stream(e4 + q, v);
       }
     } else {
       const int n = H * W;
       for (int b = lane; b < n; b += 32) {
         int row = b / W, col = b - row * W;
         uint8_t v = (uint8_t)((rows[row] >> col) & T(1));
-        dst[b] = v;
-        if (dup_off) dst[b + dup_off] = v;
+        st_stream(dst + b, v);
+        if (dup_off) st_stream(dst + b + dup_off, v);
       }
     }
   }
@@ -558,8 +571,19 @@ __device__ __forceinline__ void write_obs(const S& sh, const Params& p, Env<T>& 
   const int C = sh.C(), F = sh.F();
   const int n_comp = e.hdr->n_comp, cur = e.hdr->cur, n_pins = e.hdr->n_pins;
 
-  // all_components_feature: [h, w, x|-1, y|-1, h*w/(H*W)] (+ pin ids, spatial)
+  // Small tensors (component features, pin feature rows) are assembled in shared memory
+  // and leave the SM as full coalesced chunks: scattered 2..8-byte stores each occupy a
+  // request slot on the SM -> L2 path, which is the busiest unit of this kernel.
+  const int pnum_n = sh.pnum_n(), pcat_n = sh.pcat_n();
+  const int pins_bytes = ((pnum_n + pcat_n) * 2 + 15) & ~15;
+  int16_t* snum = reinterpret_cast<int16_t*>(e.stage);
+  int16_t* scat = snum + pnum_n;
+  float* fdst = reinterpret_cast<float*>(e.stage + pins_bytes);
   float* feat = p.out.feat + (size_t)env * sh.feat_n();
+
+  // phase A: zero the pin area; all_components_feature = [h, w, x|-1, y|-1, h*w/(H*W)]
+  // (+ pin ids of the component padded with -1, spatial)
+  if (kind >= 2) zero_smem(e.stage, pins_bytes, lane);
   if (kind != 3) {
     for (int c = lane; c < C; c += 32) {  // one lane per component row (5 floats)
       float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f, f4 = 0.f;
@@ -570,11 +594,10 @@ __device__ __forceinline__ void write_obs(const S& sh, const Params& p, Env<T>& 
         f3 = r.y == 0xFF ? -1.f : (float)r.y;
         f4 = area_ratio(sh, p, r.h * r.w);
       }
-      float* row = feat + c * 5;
+      float* row = fdst + c * 5;
       row[0] = f0; row[1] = f1; row[2] = f2; row[3] = f3; row[4] = f4;
     }
   } else {
-    float* fdst = reinterpret_cast<float*>(e.stage);
     for (int i = lane; i < sh.feat_n(); i += 32) {
       int c = i / F, f = i - F * c;
       float v = 0.f;
@@ -589,62 +612,49 @@ __device__ __forceinline__ void write_obs(const S& sh, const Params& p, Env<T>& 
       }
       fdst[i] = v;
     }
-    __syncwarp();
-    for (int q = lane; q < n_pins; q += 32) {
-      PinRec pr = e.pins[q];
-      fdst[pr.comp * F + 5 + pr.rank] = (float)pr.pin_id;
-    }
-    __syncwarp();
-    copy_out(feat, fdst, sh.feat_n() * 4, lane);
-    __syncwarp();
   }
 
-  // placement_mask / component_mask
+  // placement_mask / component_mask (consecutive bytes: already one request)
   for (int c = lane; c < C; c += 32) {
     if (kind == 1) {
-      p.out.place_mask[(size_t)env * C + c] = c < cur ? 1 : 0;       // rect:284
-      p.out.comp_mask[(size_t)env * C + c] = c < n_comp ? 1 : 0;     // rect:296-298
+      st_stream(p.out.place_mask + (size_t)env * C + c, (uint8_t)(c < cur ? 1 : 0));    // rect:284
+      st_stream(p.out.comp_mask + (size_t)env * C + c, (uint8_t)(c < n_comp ? 1 : 0));  // rect:296-298
     } else {
       uint8_t v = c >= n_comp ? 0 : (c < cur ? 2 : (c == cur ? 3 : 1));  // pin:1577-1579, 1649-1657
-      p.out.place_mask[(size_t)env * C + c] = v;
+      st_stream(p.out.place_mask + (size_t)env * C + c, v);
     }
   }
-  if (kind == 1) return;
-
-  // all_pins_num_feature / all_pins_cat_feature (pin:1521-1542, spatial:1469-1485):
-  // zero the env's slice with 16-byte stores, then every winning pin writes its row.
-  // __syncwarp() orders the two phases (they may hit the same bytes from different lanes).
-  const int pnum_n = sh.pnum_n(), pcat_n = sh.pcat_n();
-  int16_t* gnum = p.out.pnum + (size_t)env * pnum_n;
-  int16_t* gcat = p.out.pcat + (size_t)env * pcat_n;
-  if ((((pnum_n | pcat_n) * 2) & 15) == 0) {
-    uint4* z = reinterpret_cast<uint4*>(gnum);
-    for (int i = lane; i < (pnum_n >> 3); i += 32) z[i] = make_uint4(0, 0, 0, 0);
-    z = reinterpret_cast<uint4*>(gcat);
-    for (int i = lane; i < (pcat_n >> 3); i += 32) z[i] = make_uint4(0, 0, 0, 0);
-  } else {
-    uint32_t* z = reinterpret_cast<uint32_t*>(gnum);  // pnum_n is a multiple of 4 int16
-    for (int i = lane; i < (pnum_n >> 1); i += 32) z[i] = 0u;
-    for (int i = lane; i < pcat_n; i += 32) gcat[i] = 0;
-  }
   __syncwarp();
-  for (int q = lane; q < n_pins; q += 32) {
-    PinRec pr = e.pins[q];
-    if (!(pr.flags & kPinWinner)) continue;
-    CompRec r = e.comps[pr.comp];
-    int ax = r.x == 0xFF ? -1 : r.x + pr.rx;
-    int ay = r.x == 0xFF ? -1 : r.y + pr.ry;
-    int row = kind == 3 ? pr.pin_id : pr.comp * sh.P() + pr.pin_id;
-    // one 8-byte store: [rel_x, rel_y, abs_x, abs_y] as int16
-    uint2 v = make_uint2((uint32_t)pr.rx | ((uint32_t)pr.ry << 16),
-                         ((uint32_t)ax & 0xffffu) | ((uint32_t)ay << 16));
-    *reinterpret_cast<uint2*>(gnum + row * 4) = v;
-    if (kind == 3)
-      *reinterpret_cast<uint32_t*>(gcat + row * 2) = (uint32_t)pr.net | ((uint32_t)pr.comp << 16);
-    else
-      gcat[row] = pr.net;
+
+  // phase B: every winning pin writes its feature row (pin:1521-1542, spatial:1469-1485);
+  // the spatial env also lists each component's pin ids in its feature row
+  if (kind >= 2) {
+    for (int q = lane; q < n_pins; q += 32) {
+      PinRec pr = e.pins[q];
+      if (kind == 3) fdst[pr.comp * F + 5 + pr.rank] = (float)pr.pin_id;
+      if (!(pr.flags & kPinWinner)) continue;
+      CompRec r = e.comps[pr.comp];
+      int ax = r.x == 0xFF ? -1 : r.x + pr.rx;
+      int ay = r.x == 0xFF ? -1 : r.y + pr.ry;
+      int row = kind == 3 ? pr.pin_id : pr.comp * sh.P() + pr.pin_id;
+      // [rel_x, rel_y, abs_x, abs_y] as int16
+      uint2 v = make_uint2((uint32_t)pr.rx | ((uint32_t)pr.ry << 16),
+                           ((uint32_t)ax & 0xffffu) | ((uint32_t)ay << 16));
+      *reinterpret_cast<uint2*>(snum + row * 4) = v;
+      if (kind == 3)
+        *reinterpret_cast<uint32_t*>(scat + row * 2) = (uint32_t)pr.net | ((uint32_t)pr.comp << 16);
+      else
+        scat[row] = pr.net;
+    }
+    if (kind == 3 && lane == 0) { scat[pcat_n - 2] = -1; scat[pcat_n - 1] = -1; }
+    __syncwarp();
   }
-  if (kind == 3 && lane == 0) { gcat[pcat_n - 2] = -1; gcat[pcat_n - 1] = -1; }
+
+  // phase C: coalesced write-out
+  copy_out(feat, fdst, sh.feat_n() * 4, lane);
+  if (kind == 1) return;
+  copy_out(p.out.pnum + (size_t)env * pnum_n, snum, pnum_n * 2, lane);
+  copy_out(p.out.pcat + (size_t)env * pcat_n, scat, pcat_n * 2, lane);
   if (kind != 3) return;
   __syncwarp();
 
@@ -1007,11 +1017,17 @@ step_kernel(const Params p) {
   const int env = blockIdx.x * kWarpsPerCta + wic;
   const bool live = env < p.n_envs;
   // issue every global load of this warp before anything waits: table, state, action
+#if defined(PCB_EXPERIMENT_STORES_ONLY) && PCB_EXPERIMENT_STORES_ONLY == 3
+  const uint4 lut_part = make_uint4(0, 0, 0, 0);
+  const int n16 = sh.st_stride() >> 4;
+  uint4 st0 = make_uint4(1, 2, 3, 4);
+#else
   const uint4 lut_part = expand_lut_fetch();
   const uint8_t* gstate_c = p.state + (size_t)(live ? env : 0) * sh.st_stride();
   const int n16 = sh.st_stride() >> 4;
   uint4 st0 = make_uint4(0, 0, 0, 0);
   if (lane < n16) st0 = reinterpret_cast<const uint4*>(gstate_c)[lane];
+#endif
   const int kind = sh.kind();
   int o = 0, x = 0, y = 0;
   if (live) {  // FlatteningActionWrapper*: env_wrappers.py:80-98, wrapper_square.py:54-69
@@ -1028,6 +1044,35 @@ step_kernel(const Params p) {
   }
   expand_lut_store(smem, lut_part);
   if (!live) return;
+#ifdef PCB_EXPERIMENT_STORES_ONLY
+  {  // measurement only: the store pattern of one step without any of the computation
+#if PCB_EXPERIMENT_STORES_ONLY == 2
+#define PCB_XST(ptr, val) __stcs(ptr, val)
+#else
+#define PCB_XST(ptr, val) (*(ptr) = (val))
+#endif
+    const uint4 zv = make_uint4(lane, o, x, y);
+    uint4* g;
+    g = reinterpret_cast<uint4*>(p.out.grid + (size_t)env * sh.grid_b());
+    for (int i = lane; i < (sh.grid_b() >> 4); i += 32) PCB_XST(g + i, zv);
+    g = reinterpret_cast<uint4*>(p.out.mask + (size_t)env * sh.mask_b());
+    for (int i = lane; i < (sh.mask_b() >> 4); i += 32) PCB_XST(g + i, zv);
+    if (sh.kind() >= 2) {
+      g = reinterpret_cast<uint4*>(p.out.pnum + (size_t)env * sh.pnum_n());
+      for (int i = lane; i < (sh.pnum_n() >> 3); i += 32) PCB_XST(g + i, zv);
+      g = reinterpret_cast<uint4*>(p.out.pcat + (size_t)env * sh.pcat_n());
+      for (int i = lane; i < (sh.pcat_n() >> 3); i += 32) PCB_XST(g + i, zv);
+    }
+    uint32_t* f = reinterpret_cast<uint32_t*>(p.out.feat + (size_t)env * sh.feat_n());
+    for (int i = lane; i < sh.feat_n(); i += 32) f[i] = lane;
+    if (lane < sh.C()) p.out.place_mask[(size_t)env * sh.C() + lane] = 1;
+    g = reinterpret_cast<uint4*>(p.state + (size_t)env * sh.st_stride());
+    if (lane < n16) g[lane] = st0;
+    if (lane == 0) { p.out.done[env] = 0; p.out.reward[env] = 0.0; }
+    if (p.actions_out && lane == 0) { p.actions_out[3 * env] = 0; p.actions_out[3 * env + 1] = 0; p.actions_out[3 * env + 2] = 0; }
+    return;
+  }
+#endif
   Env<T> e(smem + kLutBytes + (size_t)wic * sh.sm_stride(), sh);
   uint8_t* gstate = p.state + (size_t)env * sh.st_stride();
   if (lane < n16) reinterpret_cast<uint4*>(e.sm)[lane] = st0;

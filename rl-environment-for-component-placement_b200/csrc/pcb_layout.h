@@ -113,8 +113,9 @@ PCB_HD constexpr Layout make_layout(int kind, int H, int W, int C, int mh, int m
   L.pcat_n = kind == 2 ? C * L.P : (kind == 3 ? (C * L.P + 1) * 2 : 0);
   L.pgrid_b = kind == 3 ? H * W * K : 0;
   L.cgrid_b = kind == 3 ? C * mh * mw * K : 0;
-  int stage = maxc(16, (L.pnum_n + L.pcat_n) * 2);
-  if (kind == 3) stage = maxc(maxc(stage, L.feat_n * 4), maxc(L.pgrid_b, L.cgrid_b));
+  // staging: pin feature rows + component features side by side; the spatial boards reuse it
+  int stage = align16c((L.pnum_n + L.pcat_n) * 2) + align16c(L.feat_n * 4) + 16;
+  if (kind == 3) stage = maxc(stage, maxc(L.pgrid_b, L.cgrid_b));
   L.sm_mrow = L.st_stride;
   L.sm_stage = L.sm_mrow + (fast_board ? 0 : 2 * rows * word);
   L.sm_scr = L.sm_stage;  // (unused by the step kernel; the reward kernel has its own scratch)
