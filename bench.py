@@ -321,35 +321,67 @@ def gpu_arm(args, rank, world, local_rank):
     print(json.dumps(out), flush=True)
 
 
+def _cpu_slices(args):
+    """One worker of the reference arm: (warmup + steps) consecutive time slices of the
+    random-policy loop; returns (env-steps, seconds) of every slice."""
+    name, wid, n_slices, slice_s = args
+    import random
+
+    import numpy as np
+
+    from ref_harness import CONFIGS, make_oracle
+
+    np.random.seed(wid)
+    random.seed(wid)
+    rng = np.random.default_rng(wid)
+    env = make_oracle(CONFIGS[name])
+    out = []
+    env.reset()
+    done = False
+    for _ in range(n_slices):
+        steps, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < slice_s:
+            if done:
+                env.reset()
+                done = False
+            valid = np.flatnonzero(env.action_mask)
+            a = np.unravel_index(valid[rng.integers(0, len(valid))], env.action_mask.shape)
+            _, _, done, _ = env.step(tuple(int(v) for v in a))
+            steps += 1
+        out.append((steps, time.perf_counter() - t0))
+    return out
+
+
 def reference_arm(args, rank, world):
     """The reference's CPU implementation of the path on the host cores.  The reference
     is pure Python and is not present on the GPU box, so this times the oracle port
-    (oracle/: same numpy/scipy operations per step) with one process per core."""
+    (oracle/: same numpy/scipy operations per step) with one process per core.  A "step"
+    is a bounded time slice of the rollout; W warm-up slices, K timed slices, one pool."""
     if rank != 0:
         return
     name = args.workload
     procs = os.cpu_count() or 1
     K, W = args.steps, args.warmup
-    # a "step" = a bounded sample; the whole run is sized to stay within a few minutes
-    per_step = max(0.5, min(4.0, 120.0 / max(K + W, 1)))
-    for _ in range(min(W, 1)):
-        cpu_baseline(name, 0.5, procs)
+    slice_s = max(0.02, min(2.0, 45.0 / max(K + W, 1)))
+    ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
-    rates = []
-    reps = max(1, min(K, int(120.0 / per_step)))
-    for _ in range(reps):
-        rates.append(cpu_baseline(name, per_step, procs)["value"])
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_cpu_slices, [(name, w, K + W, slice_s) for w in range(procs)])
     wall = time.perf_counter() - t0
-    value = sum(rates) / len(rates)
+    value = sum(sum(s for s, _ in r[W:]) / sum(t for _, t in r[W:]) for r in res)
+    total_steps = sum(s for r in res for s, _ in r[W:])
     out = {
         "impl": "reference", "metric": "env-steps/sec", "value": value, "unit": "env-steps/s",
-        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": per_step * 1e3,
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": slice_s * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": WORKLOAD_DESC[name], "policy": "uniform random over valid actions",
-                   "note": "CPU multiprocess vector env, %d samples of %.1f s" % (reps, per_step)},
+                   "note": "CPU multiprocess vector env; a step = a %.3f s slice of the rollout "
+                           "in each of %d processes" % (slice_s, procs)},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": procs, "kind": "port",
-                         "sample": f"{reps} x {per_step:.1f} s x {procs} processes, config {name}, wall {wall:.0f} s"},
+                         "sample": f"{K} timed slices of {slice_s:.3f} s x {procs} processes, config {name}, "
+                                   f"{total_steps} env-steps, wall {wall:.0f} s; oracle/ numpy port of the "
+                                   "reference envs (the reference is Python and absent on the GPU box)"},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
