@@ -31,13 +31,17 @@ WORKLOAD = "C"
 ENVS_PER_GPU = 65536
 OBS_RING = 4
 # SURVEY.md section 8d / BASELINE.md section 5: algorithmic bytes per env-step (compact contract)
-ALGO_BYTES = {"A": 161, "B": 1049, "C": 7699, "D": 15775, "E": 28821}
-EP_LEN = {"A": 4, "B": 6, "C": 10, "D": 10, "E": 32}
+ALGO_BYTES = {"A": 161, "B": 1049, "C": 7699, "D": 15775, "E": 28821,
+              # the reference's shipped 10x10 pin config (agent/config/rectangle_pin_model.json):
+              # grid 100 + mask 400 + features 100 + placement 5 + pins 160 + 40 + 21 + 2 * 192 state
+              "REF_pin": 1210}
+EP_LEN = {"A": 4, "B": 6, "C": 10, "D": 10, "E": 32, "REF_pin": 5}
 WORKLOAD_DESC = {
     "B": "B: dummy_env_rectangular 16x16, 6 rectangular components",
     "C": "C: dummy_env_rectangular_pin 32x32, 10 components, 5 nets, <=6 pins/net, centroid reward",
     "D": "D: dummy_env_rectangular_pin_spatial 32x32, 10 components, 5 nets, centroid reward",
     "E": "E: dummy_env_rectangular_pin 64x64, 32 components, 16 nets, centroid reward",
+    "REF_pin": "REF_pin: dummy_env_rectangular_pin 10x10, 5 components 2x2, 3 nets x 6 pins (agent/config/rectangle_pin_model.json)",
 }
 
 
@@ -174,7 +178,7 @@ def gpu_arm(args, rank, world, local_rank):
     N = args.envs
     cfg = CONFIGS[name]
     env = pcbgpu.PcbVecEnv(cfg, N, device=local_rank, autoreset=True, obs_ring=OBS_RING,
-                           bank_size=N * 4, seed=1000 + rank)
+                           bank_size=N * 4, seed=1000 + rank, generate_on_device=True)
     seed = 7 + rank
     K, W = args.steps, args.warmup
     stream = torch.cuda.current_stream()
@@ -288,7 +292,7 @@ def gpu_arm(args, rank, world, local_rank):
         "config": {
             "workload": WORKLOAD_DESC[name], "envs_per_gpu": N, "policy": "uniform random over valid "
             "actions, sampled on device (Philox)", "autoreset": True,
-            "instances": f"{N * 4} per GPU from the library generator (distribution of the reference's generate_instances)",
+            "instances": f"{N * 4} per GPU from the library's device generator (distribution of the reference's generate_instances)",
             "episode_phases": "staggered (1/%d of the envs finish every step)" % EP_LEN[name],
             "l2": "working set larger than L2: every step writes a fresh %.0f MB observation slice "
                   "(ring of %d slices)" % (N * (ALGO_BYTES[name]) / 1e6, OBS_RING),

@@ -319,7 +319,7 @@ __device__ __forceinline__ uint4 expand16(const uint2* lut, uint32_t b) {
 
 template <int RPL, typename T, typename S>
 __device__ __forceinline__ void write_board(const S& sh, uint8_t* dst, const T (&regs)[RPL],
-                                            const T* rows, int lane, int dup_off,
+                                            const T* rows, uint32_t* flat, int lane, int dup_off,
                                             const uint2* lut) {
   uint4* d4 = reinterpret_cast<uint4*>(dst);
   uint4* e4 = reinterpret_cast<uint4*>(dst + dup_off);
@@ -364,13 +364,54 @@ __device__ __forceinline__ void write_board(const S& sh, uint8_t* dst, const T (
         st_stream(d4 + q, v);
         if (dup_off) st_stream(e4 + q, v);
       }
+    } else if (((H * W) & 3) == 0) {
+      // Any other width: pack the board into one dense bit string (bit row*W + col) in
+      // shared memory -- each row ORs its bits into the one or two words it overlaps --
+      // then every lane turns 4 (or 16) consecutive bits into bytes: no per-byte index math.
+      const int nbits = H * W, nwords = (nbits + 31) >> 5;
+      for (int i = lane; i < nwords + 2; i += 32) flat[i] = 0u;
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < RPL; ++k) {
+        const int row = lane + 32 * k;
+        if (row < H && regs[k] != T(0)) {
+          const int pos = row * W, lo = pos >> 5, sh_ = pos & 31;
+          const uint64_t v = (uint64_t)regs[k];
+          const uint64_t a = v << sh_;
+          atomicOr(flat + lo, (uint32_t)a);
+          if (a >> 32) atomicOr(flat + lo + 1, (uint32_t)(a >> 32));
+          if (sizeof(T) == 8 && sh_ && (v >> (64 - sh_))) atomicOr(flat + lo + 2, (uint32_t)(v >> (64 - sh_)));
+        }
+      }
+      __syncwarp();
+      if ((nbits & 15) == 0) {
+        for (int q = lane; q < (nbits >> 4); q += 32) {
+          uint4 v = expand16(lut, flat[q >> 1] >> (16 * (q & 1)));
+          st_stream(d4 + q, v);
+          if (dup_off) st_stream(e4 + q, v);
+        }
+      } else {
+        uint32_t* d1 = reinterpret_cast<uint32_t*>(dst);
+        uint32_t* e1 = reinterpret_cast<uint32_t*>(dst + dup_off);
+        for (int q = lane; q < (nbits >> 2); q += 32) {
+          uint32_t v = spread4((flat[q >> 3] >> (4 * (q & 7))) & 15u);
+          st_stream(d1 + q, v);
+          if (dup_off) st_stream(e1 + q, v);
+        }
+      }
+      __syncwarp();
     } else {
+      // odd sizes: byte b = row * W + col; lane handles b = lane, lane + 32, ...: (row, col)
+      // advance by (32 / W, 32 % W) with a carry, so only the first position needs a division
       const int n = H * W;
+      const int q32 = 32 / W, r32 = 32 - q32 * W;
+      int row = lane / W, col = lane - row * W;
       for (int b = lane; b < n; b += 32) {
-        int row = b / W, col = b - row * W;
         uint8_t v = (uint8_t)((rows[row] >> col) & T(1));
         st_stream(dst + b, v);
         if (dup_off) st_stream(dst + b + dup_off, v);
+        row += q32; col += r32;
+        if (col >= W) { col -= W; row += 1; }
       }
     }
   }
@@ -429,14 +470,16 @@ __device__ __forceinline__ uint32_t philox_u32(uint64_t seed, uint32_t c0, uint3
 #endif
 // 1: SplitMix64 finaliser of the 64-bit counter (seed, env, step) -- ~3x fewer
 // instructions than Philox4x32-10 (0), same counter-based, stateless construction.
-__device__ __forceinline__ uint32_t action_rand(uint64_t seed, uint32_t env, uint64_t step_no) {
-#if PCB_OPT_RNG
+__device__ __forceinline__ uint64_t action_rand64(uint64_t seed, uint32_t env, uint64_t step_no) {
   uint64_t z = seed + ((step_no << 32) | (uint64_t)env) * 0x9E3779B97F4A7C15ull;
   z ^= step_no >> 32;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return (uint32_t)(z >> 32);
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint32_t action_rand(uint64_t seed, uint32_t env, uint64_t step_no) {
+#if PCB_OPT_RNG
+  return (uint32_t)(action_rand64(seed, env, step_no) >> 32);
 #else
   return philox_u32(seed, env, (uint32_t)step_no, (uint32_t)(step_no >> 32));
 #endif
@@ -460,12 +503,12 @@ __device__ __forceinline__ void sample_action(const S& sh, const T (&m0)[RPL], c
     for (int k = 0; k < RPL; ++k) anyv |= m0[k] | m1[k];
     if (__any_sync(kFull, anyv != T(0))) {
       const int H = sh.H(), W = sh.W();
-      const uint32_t cells = (uint32_t)(sh.O() * H * W);
       for (int t = 0; t < PCB_SAMPLE_TRIES; ++t) {
-        const uint32_t r = action_rand(seed + 0x632BE59BD9B4E019ull * (uint64_t)(t + 1), (uint32_t)env, step_no);
-        const int idx = (int)__umulhi(r, cells);
-        const int o = idx / (H * W), rem = idx - o * (H * W);
-        const int row = rem / W, col = rem - row * W;
+        // three independent 21-bit uniforms -> (orientation, row, column); no division
+        const uint64_t r = action_rand64(seed + 0x632BE59BD9B4E019ull * (uint64_t)(t + 1), (uint32_t)env, step_no);
+        const int o = (int)((((uint32_t)r & 0x1fffffu) * (uint32_t)sh.O()) >> 21);
+        const int row = (int)((((uint32_t)(r >> 21) & 0x1fffffu) * (uint32_t)H) >> 21);
+        const int col = (int)((((uint32_t)(r >> 42) & 0x1fffffu) * (uint32_t)W) >> 21);
         T mine = T(0);
 #pragma unroll
         for (int k = 0; k < RPL; ++k)
@@ -560,11 +603,12 @@ __device__ __forceinline__ void write_obs(const S& sh, const Params& p, Env<T>& 
   const int O = sh.O();
   extern __shared__ __align__(16) uint8_t smem_base[];
   const uint2* lut = reinterpret_cast<const uint2*>(smem_base);
-  write_board<RPL, T, S>(sh, p.out.grid + (size_t)env * sh.grid_b(), occ, e.occ, lane, 0, lut);
+  uint32_t* flat = reinterpret_cast<uint32_t*>(e.scr);
+  write_board<RPL, T, S>(sh, p.out.grid + (size_t)env * sh.grid_b(), occ, e.occ, flat, lane, 0, lut);
   uint8_t* mk = p.out.mask + (size_t)env * sh.mask_b();
-  write_board<RPL, T, S>(sh, mk, m0, e.mrow, lane, O == 4 ? 2 * HW : 0, lut);
+  write_board<RPL, T, S>(sh, mk, m0, e.mrow, flat, lane, O == 4 ? 2 * HW : 0, lut);
   if (O >= 2)
-    write_board<RPL, T, S>(sh, mk + HW, m1, e.mrow + rows, lane, O == 4 ? 2 * HW : 0, lut);
+    write_board<RPL, T, S>(sh, mk + HW, m1, e.mrow + rows, flat, lane, O == 4 ? 2 * HW : 0, lut);
   const int kind = sh.kind();
   if (kind == 0) return;
 

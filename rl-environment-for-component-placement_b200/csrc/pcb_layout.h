@@ -117,8 +117,9 @@ PCB_HD constexpr Layout make_layout(int kind, int H, int W, int C, int mh, int m
   int stage = align16c((L.pnum_n + L.pcat_n) * 2) + align16c(L.feat_n * 4) + 16;
   if (kind == 3) stage = maxc(stage, maxc(L.pgrid_b, L.cgrid_b));
   L.sm_mrow = L.st_stride;
-  L.sm_stage = L.sm_mrow + (fast_board ? 0 : 2 * rows * word);
-  L.sm_scr = L.sm_stage;  // (unused by the step kernel; the reward kernel has its own scratch)
+  // generic boards: mask rows, then a dense bit string of one board (H*W bits + slack)
+  L.sm_scr = L.sm_mrow + (fast_board ? 0 : 2 * rows * word);
+  L.sm_stage = L.sm_scr + (fast_board ? 0 : align16c(4 * ((H * W + 31) / 32 + 3)));
   L.sm_stride = align16c(L.sm_stage + align16c(stage) + 16);
   return L;
 }

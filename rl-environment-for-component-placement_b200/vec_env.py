@@ -45,7 +45,8 @@ class PcbVecEnv:
     """
 
     def __init__(self, env_config, num_envs, device=0, autoreset=True, obs_ring=1,
-                 instances=None, bank_size=None, seed=0, norm_uses_fma=True, force_generic=False):
+                 instances=None, bank_size=None, seed=0, norm_uses_fma=True, force_generic=False,
+                 generate_on_device=False):
         if not torch.cuda.is_available():
             raise RuntimeError("pcbgpu needs a CUDA device; there is no CPU fallback")
         self.lib = _lib.load()
@@ -67,7 +68,7 @@ class PcbVecEnv:
             if instances is not None:
                 self.set_instances(instances)
             else:
-                self.generate_instances(bank_size or self.num_envs, seed)
+                self.generate_instances(bank_size or self.num_envs, seed, on_device=generate_on_device)
 
     # -- lifecycle -----------------------------------------------------------
     def close(self):
