@@ -37,6 +37,7 @@ ALGO_BYTES = {"A": 161, "B": 1049, "C": 7699, "D": 15775, "E": 28821,
               "REF_pin": 1210}
 EP_LEN = {"A": 4, "B": 6, "C": 10, "D": 10, "E": 32, "REF_pin": 5}
 WORKLOAD_DESC = {
+    "A": "A: dummy_env_square 8x8, 3x3 components",
     "B": "B: dummy_env_rectangular 16x16, 6 rectangular components",
     "C": "C: dummy_env_rectangular_pin 32x32, 10 components, 5 nets, <=6 pins/net, centroid reward",
     "D": "D: dummy_env_rectangular_pin_spatial 32x32, 10 components, 5 nets, centroid reward",
@@ -223,8 +224,17 @@ def gpu_arm(args, rank, world, local_rank):
     env.rollout_random(K, seed, actions_log=log)
     barrier()
     kt = env.kernel_times()
-    env.kernel_timing(False)
     stats2 = env.episode_stats(reset=True)
+    # same again with the kernels strictly one after the other: the step kernel on its own
+    prepare()
+    env.reward_overlap(False)
+    barrier()
+    env.rollout_random(K, seed)
+    barrier()
+    kt_alone = env.kernel_times()
+    env.reward_overlap(True)
+    env.kernel_timing(False)
+    env.episode_stats(reset=True)
 
     # ---- pass 3: end to end through host buffers (e2e) ---------------------------
     import numpy as np
@@ -310,6 +320,9 @@ def gpu_arm(args, rank, world, local_rank):
                      "algorithmic_bytes_per_env_step": ALGO_BYTES[name],
                      "envs_written_per_launch": written,
                      "avg_launch_us": avg_step_s * 1e6,
+                     "alone": {"avg_launch_us": kt_alone["step"][0] * 1e3 / max(kt_alone["step"][1], 1),
+                               "frac": bytes_per_launch / (kt_alone["step"][0] * 1e-3 / max(kt_alone["step"][1], 1)) / 1e9 / peak,
+                               "note": "step_kernel timed without the reward kernel running beside it"},
                      "whole_step_frac": value / world * ALGO_BYTES[name] / 1e9 / peak,
                      "kernel_share_ms": {"step": step_ms, "reward": term_ms, "sample": samp_ms}},
         "episodes": {"device_pass": stats["episodes"], "timed_kernel_pass": stats2["episodes"],

@@ -207,6 +207,10 @@ int64_t pcb_launch_count(pcb_env_t* env);
 int pcb_rollout_random(pcb_env_t* env, uint64_t seed, int n_steps, int32_t* d_actions_log,
                        void* stream);
 
+/* pcb_rollout_random runs the reward kernel of step t concurrently with the step kernel of
+ * step t+1 (default on); 0 = strictly one after the other, as pcb_step always does. */
+int pcb_set_reward_overlap(pcb_env_t* env, int on);
+
 /* Measurement aid: when on, every kernel launch is bracketed by CUDA events on the
  * launching stream.  pcb_kernel_times waits for them and returns the summed device
  * time [ms] and launch count per kernel {step, reward, reset, sample}, then clears. */

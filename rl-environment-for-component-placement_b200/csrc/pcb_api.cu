@@ -22,6 +22,10 @@
 
 using namespace pcb;
 
+#ifndef PCB_OVERLAP_REWARD
+#define PCB_OVERLAP_REWARD 1
+#endif
+
 namespace {
 
 thread_local std::string g_err;
@@ -80,6 +84,7 @@ struct pcb_env {
   cudaStream_t side;     // stream of the overlapped reward kernels
   cudaEvent_t ev_step[2], ev_rew[2];
   bool rew_pending[2];
+  bool overlap;          // pcb_rollout_random overlaps the reward kernel with the next step
   std::vector<TensorDesc> tensors;
   std::vector<void*> allocs;
   // optional per-kernel CUDA-event timing (pcb_enable_kernel_timing)
@@ -155,6 +160,11 @@ int pick_shape(const Dims& d) {
   if (is(2, 32, 32, 10, 4, 4, 6, 30)) return 2;
   if (is(3, 32, 32, 10, 4, 4, 6, 30)) return 3;
   if (is(2, 64, 64, 32, 4, 4, 17, 96)) return 4;
+  if (is(2, 10, 10, 5, 2, 2, 4, 18)) return 5;
+  if (is(3, 10, 10, 5, 2, 2, 4, 18)) return 6;
+  if (is(1, 10, 10, 20, 4, 4, 0, 0)) return 7;
+  if (is(0, 10, 10, 0, 0, 0, 0, 0)) return 8;
+  if (is(0, 8, 8, 0, 0, 0, 0, 0)) return 9;
   return 0;
 }
 
@@ -197,6 +207,11 @@ int launch(pcb_env* e, KernelId id, const Params& p, cudaStream_t st, int reward
       case 2: launch_shape<1, uint32_t, ShapeC>(id, grid, block, sm, st, p); break;
       case 3: launch_shape<1, uint32_t, ShapeD>(id, grid, block, sm, st, p); break;
       case 4: launch_shape<2, uint64_t, ShapeE>(id, grid, block, sm, st, p); break;
+      case 5: launch_shape<1, uint32_t, ShapeRefPin>(id, grid, block, sm, st, p); break;
+      case 6: launch_shape<1, uint32_t, ShapeRefSpatial>(id, grid, block, sm, st, p); break;
+      case 7: launch_shape<1, uint32_t, ShapeRefRect>(id, grid, block, sm, st, p); break;
+      case 8: launch_shape<1, uint32_t, ShapeRefSquare>(id, grid, block, sm, st, p); break;
+      case 9: launch_shape<1, uint32_t, ShapeA>(id, grid, block, sm, st, p); break;
       default:
         if (e->wide) launch_shape<2, uint64_t, DynShape>(id, grid, block, sm, st, p);
         else launch_shape<1, uint32_t, DynShape>(id, grid, block, sm, st, p);
@@ -392,7 +407,11 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
   memset(&e->base, 0, sizeof e->base);
   fill_dims(*cfg, false, e->d);
   e->shape_id = cfg->reserved0 == 1 ? 0 : pick_shape(e->d);  // reserved0 == 1 forces the generic kernels (tests)
-  if (e->shape_id) fill_dims(*cfg, true, e->d);  // every FixedShape expands boards from registers
+  {
+    // FixedShape::fast_board: square 16/32/64 boards are expanded straight from registers
+    const int H = cfg->height, W = cfg->width;
+    if (e->shape_id && H == W && (H == 16 || H == 32 || H == 64)) fill_dims(*cfg, true, e->d);
+  }
   const Dims& d = e->d;
   e->smem_bytes = (size_t)kLutBytes + (size_t)d.L.sm_stride * kWarpsPerCta;
   if (e->smem_bytes > 200 * 1024) {
@@ -406,12 +425,17 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
     case 2: TRY((set_smem_shape<1, uint32_t, ShapeC>(e->smem_bytes))); break;
     case 3: TRY((set_smem_shape<1, uint32_t, ShapeD>(e->smem_bytes))); break;
     case 4: TRY((set_smem_shape<2, uint64_t, ShapeE>(e->smem_bytes))); break;
+    case 5: TRY((set_smem_shape<1, uint32_t, ShapeRefPin>(e->smem_bytes))); break;
+    case 6: TRY((set_smem_shape<1, uint32_t, ShapeRefSpatial>(e->smem_bytes))); break;
+    case 7: TRY((set_smem_shape<1, uint32_t, ShapeRefRect>(e->smem_bytes))); break;
+    case 8: TRY((set_smem_shape<1, uint32_t, ShapeRefSquare>(e->smem_bytes))); break;
+    case 9: TRY((set_smem_shape<1, uint32_t, ShapeA>(e->smem_bytes))); break;
     default:
       if (e->wide) TRY((set_smem_shape<2, uint64_t, DynShape>(e->smem_bytes)));
       else TRY((set_smem_shape<1, uint32_t, DynShape>(e->smem_bytes)));
   }
   e->jobs = nullptr; e->job_count = nullptr; e->reward_smem = 0; e->reward_grid = 1; e->reward_grid_side = 1;
-  e->side = nullptr; e->rew_pending[0] = e->rew_pending[1] = false;
+  e->side = nullptr; e->rew_pending[0] = e->rew_pending[1] = false; e->overlap = PCB_OVERLAP_REWARD != 0;
   for (int i = 0; i < 2; ++i) { e->ev_step[i] = nullptr; e->ev_rew[i] = nullptr; }
   if (d.kind >= 2) {
     e->reward_smem = (size_t)((route_scratch_bytes(d.max_pins, d.K) + 15) & ~15) * kWarpsPerCta;
@@ -813,9 +837,6 @@ int pcb_set_state(pcb_env_t* e, const void* h_state, uint64_t step_no, void* str
 
 int64_t pcb_launch_count(pcb_env_t* e) { return e ? e->launches : 0; }
 
-#ifndef PCB_OVERLAP_REWARD
-#define PCB_OVERLAP_REWARD 1
-#endif
 int pcb_rollout_random(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_actions_log, void* stream) {
   int rc = ready(e);
   if (rc) return rc;
@@ -832,11 +853,17 @@ int pcb_rollout_random(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_acti
     if (t + 1 < n_steps)
       nxt = d_actions_log ? d_actions_log + (size_t)(t + 1) * per
                           : (cur == e->d_actions ? e->d_actions2 : e->d_actions);
-    rc = step_impl(e, cur, PCB_ACTION_TUPLE, seed, nxt, stream, PCB_OVERLAP_REWARD != 0);
+    rc = step_impl(e, cur, PCB_ACTION_TUPLE, seed, nxt, stream, e->overlap);
     if (rc) return rc;
     cur = nxt;
   }
   return join_rewards(e, (cudaStream_t)stream);
+}
+
+int pcb_set_reward_overlap(pcb_env_t* e, int on) {
+  if (!e) return fail(PCB_ERR_INVALID, "env is NULL");
+  e->overlap = on != 0;
+  return 0;
 }
 
 int pcb_enable_kernel_timing(pcb_env_t* e, int on) {

@@ -70,10 +70,16 @@ struct DynShape {
 };
 
 // the canonical configurations of BASELINE.md section 2
+using ShapeA = FixedShape<0, 8, 8, 0, 0, 0, 0, 0>;
 using ShapeB = FixedShape<1, 16, 16, 6, 4, 4, 0, 0>;
 using ShapeC = FixedShape<2, 32, 32, 10, 4, 4, 6, 30>;
 using ShapeD = FixedShape<3, 32, 32, 10, 4, 4, 6, 30>;
 using ShapeE = FixedShape<2, 64, 64, 32, 4, 4, 17, 96>;
+// the reference's shipped 10x10 configurations (agent/config/*.json)
+using ShapeRefPin = FixedShape<2, 10, 10, 5, 2, 2, 4, 18>;      // rectangle_pin_model.json & co.
+using ShapeRefSpatial = FixedShape<3, 10, 10, 5, 2, 2, 4, 18>;  // rectangle_pin_spatial_model.json
+using ShapeRefRect = FixedShape<1, 10, 10, 20, 4, 4, 0, 0>;     // rectangle_model.json
+using ShapeRefSquare = FixedShape<0, 10, 10, 0, 0, 0, 0, 0>;    // square_model.json
 
 // ---------------------------------------------------------------------------
 // small helpers

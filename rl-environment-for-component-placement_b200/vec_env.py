@@ -163,6 +163,10 @@ class PcbVecEnv:
         _lib.check(self.lib.pcb_rollout_random(self._h, ctypes.c_uint64(seed), int(n_steps), ptr,
                                                self._stream()))
 
+    def reward_overlap(self, on):
+        """rollout_random: run the reward kernel of step t alongside the step kernel of t+1."""
+        _lib.check(self.lib.pcb_set_reward_overlap(self._h, 1 if on else 0))
+
     def kernel_timing(self, on):
         _lib.check(self.lib.pcb_enable_kernel_timing(self._h, 1 if on else 0))
 

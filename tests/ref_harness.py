@@ -178,3 +178,10 @@ def pick_action(rng, mask, p_invalid=0.0):
     if len(valid) == 0:
         return tuple(0 for _ in mask.shape)
     return tuple(int(v) for v in valid[rng.integers(0, len(valid))])
+
+# the reference's other shipped configurations (agent/config/*.json), all 10x10
+CONFIGS["REF_spatial"] = dict(CONFIGS["REF_pin"], type="rectangle_spatial_pin")
+CONFIGS["REF_rect"] = dict(type="rectangle", height=10, width=10, min_component_w=2,
+                           min_component_h=2, max_component_w=4, max_component_h=4,
+                           max_num_components=20, min_num_components=20)
+CONFIGS["REF_square"] = dict(type="square", height=10, width=10, component_n=2)

@@ -62,3 +62,14 @@ def test_wide_grids_runtime_shaped(name):
     run_parity(name, range(n, n + 12), p_invalid=0.1, stats=st)
     run_parity(name, range(8), autoreset=True, episodes=2, stats=st)
     assert st["reward_inexact"] == 0, st
+
+
+@pytest.mark.parametrize("name", ["REF_pin", "REF_spatial", "REF_rect", "REF_square"])
+def test_reference_shipped_configs(name):
+    """agent/config/*.json (10x10): compiled as FixedShape without the fast board path."""
+    st = {}
+    run_parity(name, range(32), extra_steps=2, stats=st)
+    run_parity(name, range(32, 48), p_invalid=0.15, stats=st)
+    run_parity(name, range(16), autoreset=True, episodes=3, stats=st)
+    run_parity(name, range(8), force_generic=True, stats=st)
+    assert st["reward_inexact"] == 0, st

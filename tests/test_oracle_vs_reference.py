@@ -95,3 +95,8 @@ def test_wide_grids(name):
 
 def test_wide_square():
     run_pair("S_wide_sq", range(2))
+
+
+@pytest.mark.parametrize("name", ["REF_spatial", "REF_rect", "REF_square"])
+def test_reference_shipped_configs(name):
+    run_pair(name, range(20), extra_steps=2)
