@@ -217,6 +217,11 @@ int pcb_set_reward_overlap(pcb_env_t* env, int on);
 int pcb_enable_kernel_timing(pcb_env_t* env, int on);
 int pcb_kernel_times(pcb_env_t* env, double ms[4], int64_t launches[4]);
 
+/* Which kernel instantiation the handle uses: 0 = runtime-shaped (any configuration),
+ * 1..99 = a built-in compile-time shape (the canonical and the reference's shipped
+ * configurations), 100 = the shape this library was specialised for at build time. */
+int pcb_shape_id(pcb_env_t* env);
+
 const char* pcb_last_error(void);
 int pcb_abi_version(void);
 

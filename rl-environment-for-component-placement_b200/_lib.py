@@ -13,7 +13,7 @@ SYMBOLS = (
     "pcb_current_slice", "pcb_episode_stats", "pcb_get_occupancy", "pcb_launch_count",
     "pcb_last_error", "pcb_abi_version", "pcb_rollout_random", "pcb_enable_kernel_timing",
     "pcb_kernel_times", "pcb_current_result_half", "pcb_generate_host", "pcb_generate_instances_device", "pcb_state_layout", "pcb_get_state",
-    "pcb_set_state", "pcb_set_reward_overlap",
+    "pcb_set_state", "pcb_set_reward_overlap", "pcb_shape_id",
 )
 
 
@@ -44,22 +44,23 @@ class PcbInstanceBank(ctypes.Structure):
     ]
 
 
-_lib = None
+_libs = {}
 
 
-def load():
-    """Loads libpcbgpu.so once; raises with the build hint when it is missing."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
+def load(path=None):
+    """Loads libpcbgpu.so (or a specialised build of it) once; raises with the build hint
+    when it is missing."""
+    path = path or LIB_PATH
+    if path in _libs:
+        return _libs[path]
+    if not os.path.exists(path):
         raise ImportError(
-            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; "
             "g.build()'` (nvcc, sm_100a).  pcbgpu has no CPU fallback.")
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     for name in SYMBOLS:
         if not hasattr(lib, name):
-            raise ImportError(f"{LIB_PATH} does not export {name}; rebuild the library")
+            raise ImportError(f"{path} does not export {name}; rebuild the library")
     vp, i32, i64, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint64
     lib.pcb_create.argtypes = [ctypes.POINTER(PcbConfig), i32, i32, ctypes.POINTER(vp)]
     lib.pcb_destroy.argtypes = [vp]
@@ -87,19 +88,47 @@ def load():
     lib.pcb_kernel_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
     lib.pcb_last_error.restype = ctypes.c_char_p
     lib.pcb_abi_version.restype = i32
+    lib.pcb_shape_id.argtypes = [vp]
     if lib.pcb_abi_version() != ABI_VERSION:
         raise ImportError(f"libpcbgpu ABI {lib.pcb_abi_version()} != {ABI_VERSION}; rebuild")
-    _lib = lib
+    _libs[path] = lib
     return lib
+
+
+def specialized_library(spec, build=True):
+    """Path of a libpcbgpu build whose kernels have every dimension of ``spec`` as a
+    compile-time constant (-DPCB_US_KIND=.. -DPCB_US_H=.. ...); compiled with nvcc on first use
+    (about a minute) and cached next to the default library."""
+    import subprocess
+
+    from .config import KINDS
+
+    c = spec.c
+    K = c.max_num_nets + 1 if KINDS[spec.kind] >= 2 else 0
+    dims = (KINDS[spec.kind], c.height, c.width, c.max_num_components, c.max_component_h,
+            c.max_component_w, K, c.max_pins if KINDS[spec.kind] >= 2 else 0)
+    path = os.path.join(_HERE, "libpcbgpu_shape_" + "_".join(str(d) for d in dims) + ".so")
+    src = [os.path.join(_HERE, "csrc", n) for n in ("pcb_api.cu", "pcb_gen.cpp")]
+    newest = max(os.path.getmtime(os.path.join(_HERE, "csrc", n)) for n in os.listdir(
+        os.path.join(_HERE, "csrc")))
+    if not os.path.exists(path) or os.path.getmtime(path) < newest:
+        if not build:
+            raise ImportError(f"{path} is not built")
+        cmd = [os.environ.get("NVCC", "nvcc"), "-gencode", "arch=compute_100a,code=sm_100a",
+               "-lineinfo", "-O3", "-fmad=false", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+               ] + [f"-DPCB_US_{n}={d}" for n, d in zip(
+                   ("KIND", "H", "W", "C", "MH", "MW", "K", "PINS"), dims)] + ["-o", path] + src
+        subprocess.check_call(cmd)
+    return path
 
 
 class PcbError(RuntimeError):
     pass
 
 
-def check(rc):
+def check(rc, lib=None):
     if rc < 0:
-        msg = load().pcb_last_error()
+        msg = (lib or load()).pcb_last_error()
         raise PcbError(f"libpcbgpu error {rc}: {msg.decode() if msg else '?'}")
     return rc
 
@@ -109,10 +138,11 @@ _PyCapsule_New.restype = ctypes.py_object
 _PyCapsule_New.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p]
 
 
-def tensor(handle, key):
+def tensor(handle, key, lib=None):
     """pcb_get_tensor -> torch tensor sharing the library's device memory."""
     import torch.utils.dlpack
 
+    lib = lib or load()
     out = ctypes.c_void_p()
-    check(load().pcb_get_tensor(handle, key.encode(), ctypes.byref(out)))
+    check(lib.pcb_get_tensor(handle, key.encode(), ctypes.byref(out)), lib)
     return torch.utils.dlpack.from_dlpack(_PyCapsule_New(out, b"dltensor", None))

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/pcb_env.h"
@@ -165,6 +166,12 @@ int pick_shape(const Dims& d) {
   if (is(1, 10, 10, 20, 4, 4, 0, 0)) return 7;
   if (is(0, 10, 10, 0, 0, 0, 0, 0)) return 8;
   if (is(0, 8, 8, 0, 0, 0, 0, 0)) return 9;
+#ifdef PCB_USER_SHAPE
+  {
+    const int u[8] = {PCB_USER_SHAPE};
+    if (is(u[0], u[1], u[2], u[3], u[4], u[5], u[6], u[7])) return 100;
+  }
+#endif
   return 0;
 }
 
@@ -177,6 +184,13 @@ int launch_shape(KernelId id, dim3 grid, dim3 block, size_t sm, cudaStream_t st,
   }
   return 0;
 }
+
+#ifdef PCB_USER_SHAPE
+constexpr int kUserDims[8] = {PCB_USER_SHAPE};
+constexpr bool kUserWide = kUserDims[1] > 32 || kUserDims[2] > 32;
+using UserWord = std::conditional_t<kUserWide, uint64_t, uint32_t>;
+constexpr int kUserRpl = kUserWide ? 2 : 1;
+#endif
 
 template <int RPL, typename T, typename S>
 int set_smem_shape(size_t bytes) {
@@ -212,6 +226,9 @@ int launch(pcb_env* e, KernelId id, const Params& p, cudaStream_t st, int reward
       case 7: launch_shape<1, uint32_t, ShapeRefRect>(id, grid, block, sm, st, p); break;
       case 8: launch_shape<1, uint32_t, ShapeRefSquare>(id, grid, block, sm, st, p); break;
       case 9: launch_shape<1, uint32_t, ShapeA>(id, grid, block, sm, st, p); break;
+#ifdef PCB_USER_SHAPE
+      case 100: launch_shape<kUserRpl, UserWord, ShapeUser>(id, grid, block, sm, st, p); break;
+#endif
       default:
         if (e->wide) launch_shape<2, uint64_t, DynShape>(id, grid, block, sm, st, p);
         else launch_shape<1, uint32_t, DynShape>(id, grid, block, sm, st, p);
@@ -388,6 +405,9 @@ extern "C" {
 const char* pcb_last_error(void) { return g_err.c_str(); }
 int pcb_abi_version(void) { return PCB_ABI_VERSION; }
 
+/* 0 = runtime-shaped kernels, otherwise the id of the compiled FixedShape in use */
+int pcb_shape_id(pcb_env_t* e) { return e ? e->shape_id : -1; }
+
 int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** out) {
   if (!out) return fail(PCB_ERR_INVALID, "out is NULL");
   *out = nullptr;
@@ -430,6 +450,9 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
     case 7: TRY((set_smem_shape<1, uint32_t, ShapeRefRect>(e->smem_bytes))); break;
     case 8: TRY((set_smem_shape<1, uint32_t, ShapeRefSquare>(e->smem_bytes))); break;
     case 9: TRY((set_smem_shape<1, uint32_t, ShapeA>(e->smem_bytes))); break;
+#ifdef PCB_USER_SHAPE
+    case 100: TRY((set_smem_shape<kUserRpl, UserWord, ShapeUser>(e->smem_bytes))); break;
+#endif
     default:
       if (e->wide) TRY((set_smem_shape<2, uint64_t, DynShape>(e->smem_bytes)));
       else TRY((set_smem_shape<1, uint32_t, DynShape>(e->smem_bytes)));

@@ -75,6 +75,11 @@ using ShapeB = FixedShape<1, 16, 16, 6, 4, 4, 0, 0>;
 using ShapeC = FixedShape<2, 32, 32, 10, 4, 4, 6, 30>;
 using ShapeD = FixedShape<3, 32, 32, 10, 4, 4, 6, 30>;
 using ShapeE = FixedShape<2, 64, 64, 32, 4, 4, 17, 96>;
+// one more shape chosen at build time: -DPCB_USER_SHAPE=kind,H,W,C,mh,mw,K,max_pins
+// (pcbgpu.specialize builds such a library for any configuration)
+#ifdef PCB_USER_SHAPE
+using ShapeUser = FixedShape<PCB_USER_SHAPE>;
+#endif
 // the reference's shipped 10x10 configurations (agent/config/*.json)
 using ShapeRefPin = FixedShape<2, 10, 10, 5, 2, 2, 4, 18>;      // rectangle_pin_model.json & co.
 using ShapeRefSpatial = FixedShape<3, 10, 10, 5, 2, 2, 4, 18>;  // rectangle_pin_spatial_model.json

@@ -22,6 +22,11 @@
 #define PCB_HD
 #endif
 
+// nvcc splits -D values at commas, so a build-time shape arrives as eight macros
+#if defined(PCB_US_KIND) && !defined(PCB_USER_SHAPE)
+#define PCB_USER_SHAPE PCB_US_KIND, PCB_US_H, PCB_US_W, PCB_US_C, PCB_US_MH, PCB_US_MW, PCB_US_K, PCB_US_PINS
+#endif
+
 namespace pcb {
 
 constexpr int kMaxGrid = 64;        // H, W <= 64

@@ -46,11 +46,13 @@ class PcbVecEnv:
 
     def __init__(self, env_config, num_envs, device=0, autoreset=True, obs_ring=1,
                  instances=None, bank_size=None, seed=0, norm_uses_fma=True, force_generic=False,
-                 generate_on_device=False):
+                 generate_on_device=False, specialize=False):
         if not torch.cuda.is_available():
             raise RuntimeError("pcbgpu needs a CUDA device; there is no CPU fallback")
-        self.lib = _lib.load()
         self.spec = make_spec(env_config, autoreset, obs_ring, norm_uses_fma)
+        # specialize=True: kernels compiled for exactly this configuration (nvcc, cached);
+        # otherwise built-in shapes for the canonical configs, runtime-shaped kernels else
+        self.lib = _lib.load(_lib.specialized_library(self.spec) if specialize else None)
         if force_generic:  # use the runtime-shaped kernels even for a canonical shape (tests)
             self.spec.c.reserved0 = 1
         self.kind = self.spec.kind
@@ -58,10 +60,10 @@ class PcbVecEnv:
         self.device = torch.device("cuda", int(device))
         self.autoreset = bool(autoreset)
         self._h = ctypes.c_void_p()
-        _lib.check(self.lib.pcb_create(ctypes.byref(self.spec.c), int(device), self.num_envs,
+        self._check(self.lib.pcb_create(ctypes.byref(self.spec.c), int(device), self.num_envs,
                                        ctypes.byref(self._h)))
-        self._ring = {k: _lib.tensor(self._h, k) for k in OBS_KEYS[self.kind]}
-        self._res = {k: _lib.tensor(self._h, k) for k in RESULT_KEYS}
+        self._ring = {k: _lib.tensor(self._h, k, self.lib) for k in OBS_KEYS[self.kind]}
+        self._res = {k: _lib.tensor(self._h, k, self.lib) for k in RESULT_KEYS}
         self._actions = torch.zeros((self.num_envs, self.spec.action_width), dtype=torch.int32,
                                     device=self.device)
         if self.kind != "square":
@@ -69,6 +71,9 @@ class PcbVecEnv:
                 self.set_instances(instances)
             else:
                 self.generate_instances(bank_size or self.num_envs, seed, on_device=generate_on_device)
+
+    def _check(self, rc):
+        return _lib.check(rc, self.lib)
 
     # -- lifecycle -----------------------------------------------------------
     def close(self):
@@ -91,7 +96,7 @@ class PcbVecEnv:
         bank = instances if isinstance(instances, InstanceBank) else InstanceBank.from_list(
             self.spec, list(instances))
         s = bank.as_struct()
-        _lib.check(self.lib.pcb_upload_instances(self._h, ctypes.byref(s)))
+        self._check(self.lib.pcb_upload_instances(self._h, ctypes.byref(s)))
         self.bank_size = bank.count
 
     def generate_instances(self, count, seed=0, on_device=False):
@@ -100,10 +105,10 @@ class PcbVecEnv:
         to keep the environments on fresh instances)."""
         arr = (ctypes.c_int32 * 12)(*self.spec.generator_ranges())
         if on_device:
-            _lib.check(self.lib.pcb_generate_instances_device(
+            self._check(self.lib.pcb_generate_instances_device(
                 self._h, arr, ctypes.c_uint64(seed), ctypes.c_int64(count), self._stream()))
         else:
-            _lib.check(self.lib.pcb_generate_instances(self._h, arr, ctypes.c_uint64(seed),
+            self._check(self.lib.pcb_generate_instances(self._h, arr, ctypes.c_uint64(seed),
                                                        ctypes.c_int64(count)))
         self.bank_size = int(count)
 
@@ -118,7 +123,7 @@ class PcbVecEnv:
         if mask is not None:
             mask = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
             ptr = ctypes.c_void_p(mask.data_ptr())
-        _lib.check(self.lib.pcb_reset(self._h, ptr, self._stream()))
+        self._check(self.lib.pcb_reset(self._h, ptr, self._stream()))
         return self._obs()
 
     def step_async(self, actions):
@@ -135,7 +140,7 @@ class PcbVecEnv:
                                  f"{self.spec.action_width}] or [{self.num_envs}]")
             fmt = 0
         self._last_actions = a  # keep alive until the kernels ran
-        _lib.check(self.lib.pcb_step(self._h, ctypes.c_void_p(a.data_ptr()), fmt, self._stream()))
+        self._check(self.lib.pcb_step(self._h, ctypes.c_void_p(a.data_ptr()), fmt, self._stream()))
 
     def results(self):
         """reward, done and the info tensors of the step that just ran ([N] views)."""
@@ -152,7 +157,7 @@ class PcbVecEnv:
     def sample_random_actions(self, seed=0, out=None):
         """agent/random/random_policy_*.py on device: uniform over the valid actions."""
         out = self._actions if out is None else out
-        _lib.check(self.lib.pcb_sample_random_actions(
+        self._check(self.lib.pcb_sample_random_actions(
             self._h, ctypes.c_uint64(seed), ctypes.c_void_p(out.data_ptr()), self._stream()))
         return out
 
@@ -160,27 +165,27 @@ class PcbVecEnv:
         """n_steps of {device random policy; step} from one C call (simulate() of
         agent/random/*.py).  actions_log: optional int32 [n_steps, N, k] device tensor."""
         ptr = None if actions_log is None else ctypes.c_void_p(actions_log.data_ptr())
-        _lib.check(self.lib.pcb_rollout_random(self._h, ctypes.c_uint64(seed), int(n_steps), ptr,
+        self._check(self.lib.pcb_rollout_random(self._h, ctypes.c_uint64(seed), int(n_steps), ptr,
                                                self._stream()))
 
     def reward_overlap(self, on):
         """rollout_random: run the reward kernel of step t alongside the step kernel of t+1."""
-        _lib.check(self.lib.pcb_set_reward_overlap(self._h, 1 if on else 0))
+        self._check(self.lib.pcb_set_reward_overlap(self._h, 1 if on else 0))
 
     def kernel_timing(self, on):
-        _lib.check(self.lib.pcb_enable_kernel_timing(self._h, 1 if on else 0))
+        self._check(self.lib.pcb_enable_kernel_timing(self._h, 1 if on else 0))
 
     def kernel_times(self):
         """{kernel: (total ms, launches)} since the last call; needs kernel_timing(True)."""
         ms = (ctypes.c_double * 4)()
         n = (ctypes.c_int64 * 4)()
-        _lib.check(self.lib.pcb_kernel_times(self._h, ms, n))
+        self._check(self.lib.pcb_kernel_times(self._h, ms, n))
         return {k: (ms[i], int(n[i])) for i, k in enumerate(("step", "reward", "reset", "sample"))}
 
     def step_host(self, actions_np, reward_np, done_np):
         """step() through host buffers (pcb_step_host): H2D actions, D2H reward/done."""
         fmt = 1 if actions_np.ndim == 1 else 0
-        _lib.check(self.lib.pcb_step_host(
+        self._check(self.lib.pcb_step_host(
             self._h, ctypes.c_void_p(actions_np.ctypes.data), fmt,
             ctypes.c_void_p(reward_np.ctypes.data), ctypes.c_void_p(done_np.ctypes.data),
             self._stream()))
@@ -207,14 +212,14 @@ class PcbVecEnv:
     def occupancy(self):
         """[N, 64] uint64 bitboard rows (bit j of row r = grid[r, j])."""
         rows = np.zeros((self.num_envs, 64), np.uint64)
-        _lib.check(self.lib.pcb_get_occupancy(self._h, ctypes.c_void_p(rows.ctypes.data),
+        self._check(self.lib.pcb_get_occupancy(self._h, ctypes.c_void_p(rows.ctypes.data),
                                               self._stream()))
         return rows
 
     # -- checkpoint / inspection ---------------------------------------------
     def state_layout(self):
         out = (ctypes.c_int32 * 8)()
-        _lib.check(self.lib.pcb_state_layout(self._h, out))
+        self._check(self.lib.pcb_state_layout(self._h, out))
         keys = ("stride", "off_comps", "off_pins", "off_board", "max_comps", "max_pins",
                 "word_bytes", "rows")
         return dict(zip(keys, list(out)))
@@ -225,7 +230,7 @@ class PcbVecEnv:
         lay = self.state_layout()
         buf = np.zeros((self.num_envs, lay["stride"]), np.uint8)
         step = ctypes.c_uint64()
-        _lib.check(self.lib.pcb_get_state(self._h, ctypes.c_void_p(buf.ctypes.data),
+        self._check(self.lib.pcb_get_state(self._h, ctypes.c_void_p(buf.ctypes.data),
                                           ctypes.byref(step), self._stream()))
         return {"state": buf, "step_no": int(step.value), "kind": self.kind}
 
@@ -233,7 +238,7 @@ class PcbVecEnv:
         buf = np.ascontiguousarray(sd["state"], np.uint8)
         if buf.shape != (self.num_envs, self.state_layout()["stride"]) or sd["kind"] != self.kind:
             raise ValueError("state_dict does not match this environment")
-        _lib.check(self.lib.pcb_set_state(self._h, ctypes.c_void_p(buf.ctypes.data),
+        self._check(self.lib.pcb_set_state(self._h, ctypes.c_void_p(buf.ctypes.data),
                                           ctypes.c_uint64(sd["step_no"]), self._stream()))
 
     def decode_state(self, sd=None):
@@ -261,10 +266,15 @@ class PcbVecEnv:
 
     def episode_stats(self, reset=False):
         out = (ctypes.c_double * 8)()
-        _lib.check(self.lib.pcb_episode_stats(self._h, out, 1 if reset else 0, self._stream()))
+        self._check(self.lib.pcb_episode_stats(self._h, out, 1 if reset else 0, self._stream()))
         keys = ("episodes", "sum_return", "sum_length", "sum_wirelength", "sum_intersections",
                 "steps")
         return {k: out[i] for i, k in enumerate(keys)}
+
+    @property
+    def shape_id(self):
+        """0 = runtime-shaped kernels, 1..99 = built-in compile-time shape, 100 = specialised"""
+        return int(self.lib.pcb_shape_id(self._h))
 
     @property
     def launch_count(self):

@@ -247,3 +247,16 @@ def test_export_in_reference_pickle_format(tmp_path):
             ph, pw = (c.h, c.w) if o in (0, 2) else (c.w, c.h)
             for pin in c.pins:  # pins lie inside the placed footprint
                 assert x <= pin.absolute_x < x + ph and y <= pin.absolute_y < y + pw
+
+
+def test_specialised_library_for_an_arbitrary_config():
+    """pcbgpu can compile the kernels for exactly one configuration (-DPCB_USER_SHAPE);
+    the result must be bit-identical to the oracle like every other build."""
+    env = make("S_pin", 8, specialize=True)
+    assert env.shape_id == 100
+    env.close()
+    assert make("S_pin", 8).shape_id == 0 and make("C", 8).shape_id == 2
+    st = {}
+    run_parity("S_pin", range(32), extra_steps=2, stats=st, specialize=True)
+    run_parity("S_pin", range(16), autoreset=True, episodes=2, p_invalid=0.1, stats=st, specialize=True)
+    assert st["reward_inexact"] == 0
