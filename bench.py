@@ -34,14 +34,16 @@ OBS_RING = 4
 ALGO_BYTES = {"A": 161, "B": 1049, "C": 7699, "D": 15775, "E": 28821,
               # the reference's shipped 10x10 pin config (agent/config/rectangle_pin_model.json):
               # grid 100 + mask 400 + features 100 + placement 5 + pins 160 + 40 + 21 + 2 * 192 state
-              "REF_pin": 1210}
-EP_LEN = {"A": 4, "B": 6, "C": 10, "D": 10, "E": 32, "REF_pin": 5}
+              "REF_pin": 1210, "C_both": 7699, "C_beam": 7699}
+EP_LEN = {"A": 4, "B": 6, "C": 10, "D": 10, "E": 32, "REF_pin": 5, "C_both": 10, "C_beam": 10}
 WORKLOAD_DESC = {
     "A": "A: dummy_env_square 8x8, 3x3 components",
     "B": "B: dummy_env_rectangular 16x16, 6 rectangular components",
     "C": "C: dummy_env_rectangular_pin 32x32, 10 components, 5 nets, <=6 pins/net, centroid reward",
     "D": "D: dummy_env_rectangular_pin_spatial 32x32, 10 components, 5 nets, centroid reward",
     "E": "E: dummy_env_rectangular_pin 64x64, 32 components, 16 nets, centroid reward",
+    "C_both": "C_both: as C with reward_type='both' (beam-search route + centroid route)",
+    "C_beam": "C_beam: as C with reward_type='beam'",
     "REF_pin": "REF_pin: dummy_env_rectangular_pin 10x10, 5 components 2x2, 3 nets x 6 pins (agent/config/rectangle_pin_model.json)",
 }
 

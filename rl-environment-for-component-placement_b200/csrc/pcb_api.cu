@@ -137,7 +137,7 @@ Params make_params(const pcb_env* e, bool for_reset = false) {
   p.stats = e->stats;
   p.step_no = e->step_no;
   p.ratio_lut = e->ratio_lut;
-  p.jobs = e->jobs ? e->jobs + (size_t)parity * e->n_envs * job_stride(e->d.max_pins) : nullptr;
+  p.jobs = e->jobs ? e->jobs + (size_t)parity * e->n_envs * job_stride(e->d.max_pins, e->d.K) : nullptr;
   p.job_count = e->job_count;
   return p;
 }
@@ -210,8 +210,13 @@ int launch(pcb_env* e, KernelId id, const Params& p, cudaStream_t st, int reward
   }
   if (id == K_TERM) {
     dim3 rgrid(reward_grid > 0 ? reward_grid : e->reward_grid);
-    if (e->d.reward_type == PCB_REWARD_CENTROID) reward_kernel<false><<<rgrid, block, e->reward_smem, st>>>(p);
-    else reward_kernel<true><<<rgrid, block, e->reward_smem, st>>>(p);
+    if (e->d.reward_type == PCB_REWARD_CENTROID) {
+      reward_kernel<false><<<rgrid, block, e->reward_smem, st>>>(p);
+    } else {
+      beam_kernel<<<rgrid, 128, 0, st>>>(p);  // thread per (job, net); paths go into the jobs
+      e->launches += 1;
+      reward_kernel<true><<<rgrid, block, e->reward_smem, st>>>(p);
+    }
   } else if (id == K_SAMPLE) {
     if (e->wide) sample_kernel<2, uint64_t><<<grid, block, sm, st>>>(p);
     else sample_kernel<1, uint32_t><<<grid, block, sm, st>>>(p);
@@ -491,7 +496,7 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
   TRY(dev_alloc(e, &e->d_actions, N * 3 * sizeof(int32_t)));
   TRY(dev_alloc(e, &e->d_actions2, N * 3 * sizeof(int32_t)));
   if (d.kind >= 2) {
-    TRY(dev_alloc(e, &e->jobs, 2 * N * (size_t)job_stride(d.max_pins)));
+    TRY(dev_alloc(e, &e->jobs, 2 * N * (size_t)job_stride(d.max_pins, d.K)));
     TRY(dev_alloc(e, &e->job_count, 4 * sizeof(uint32_t)));
   }
   {

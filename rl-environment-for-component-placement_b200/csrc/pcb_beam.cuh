@@ -124,98 +124,121 @@ __device__ __forceinline__ bool beam_less(const BeamItem& a, const BeamItem& b, 
   return false;
 }
 
-// Routes every net; fills rs.start[net] and rs.nxt[pin] (global pin indices).
-__device__ __noinline__ void beam_paths(const Dims& d, const RouteScratch& rs, int lane,
-                                        int n_nets) {
-  const int bw = d.beam_width;
-  for (int net = lane; net < n_nets; net += 32) {
-    const int lo = rs.net_off[net], m_all = rs.net_off[net + 1] - lo;
-    // pin_outlier: first farthest pin from the centroid
-    int start = 0;
-    {
-      double best = -1.0;
-      const double cx = rs.cx[net], cy = rs.cy[net];
-      for (int i = 0; i < m_all; ++i) {
-        double v = norm2((double)rs.px[lo + i] - cx, (double)rs.py[lo + i] - cy, d.norm_fma);
-        if (v > best) { best = v; start = i; }
-      }
-    }
-    // points = net pins without the start (list.remove keeps the order)
-    int16_t x[kMaxBeamPoints + 1], y[kMaxBeamPoints + 1];
-    uint16_t gid[kMaxBeamPoints + 1];
-    uint64_t h[kMaxBeamPoints + 1];
-    int m = 0;
+// Routes one net: pins[lo .. lo+m_all) of a routing job.  Writes the path as a linked list
+// over the job's pin indices (nxt[pin], 0xFFFF = end) and the index of its first pin.
+__device__ __forceinline__ void beam_route_net(const JobPin* pins, int lo, int m_all, int bw,
+                                               int norm_fma, uint16_t* nxt, uint16_t* start_out) {
+  // get_centroid (exact integer sums, one division per coordinate), then pin_outlier:
+  // the first farthest pin from the centroid
+  int sxi = 0, syi = 0;
+  for (int i = 0; i < m_all; ++i) { sxi += pins[lo + i].x; syi += pins[lo + i].y; }
+  const double cx = (double)sxi / (double)m_all, cy = (double)syi / (double)m_all;
+  int start = 0;
+  {
+    double best = -1.0;
     for (int i = 0; i < m_all; ++i) {
-      if (i == start) continue;
-      x[m] = rs.px[lo + i]; y[m] = rs.py[lo + i]; gid[m] = (uint16_t)(lo + i);
-      h[m] = py_tuple_hash(x[m], y[m]);
-      ++m;
+      double v = norm2((double)pins[lo + i].x - cx, (double)pins[lo + i].y - cy, norm_fma);
+      if (v > best) { best = v; start = i; }
     }
-    const int sx = rs.px[lo + start], sy = rs.py[lo + start];
-    PyTab targets;
-    tab_clear(targets, 8);
-    for (int k = 0; k < m; ++k) tab_add(targets, k, h);
-    const uint32_t all = m >= 32 ? ~0u : ((1u << m) - 1u);
-
-    BeamItem q[kMaxBeamWidth * kMaxBeamWidth], nq[kMaxBeamWidth * kMaxBeamWidth];
-    int qn = 1;
-    q[0].prio = 0.0; q[0].seen = 0u;
-    int best_idx = 0;
-    for (int level = 0; level <= m; ++level) {  // level == number of visited points
-      // order the queue (selection of the min(bw, qn) smallest entries)
-      int order[kMaxBeamWidth];
-      int take = bw < qn ? bw : qn;
-      uint32_t used = 0;
-      for (int t = 0; t < take; ++t) {
-        int bi = -1;
-        for (int i = 0; i < qn; ++i) {
-          if ((used >> i) & 1u) continue;
-          if (bi < 0 || beam_less(q[i], q[bi], level, x, y)) bi = i;
-        }
-        used |= 1u << bi;
-        order[t] = bi;
-      }
-      if (level == m) { best_idx = order[0]; break; }  // first popped complete path wins
-      int nn = 0;
-      for (int t = 0; t < take; ++t) {
-        const BeamItem& it = q[order[t]];
-        const int hx = level ? x[it.path[level - 1]] : sx, hy = level ? y[it.path[level - 1]] : sy;
-        int8_t cand[kMaxBeamPoints + 1];
-        double cd[kMaxBeamPoints + 1];
-        int nc = tab_difference(targets, it.seen, h, cand);
-        for (int i = 0; i < nc; ++i)
-          cd[i] = norm2((double)(hx - x[cand[i]]), (double)(hy - y[cand[i]]), d.norm_fma);
-        // stable insertion sort by distance (sorted(..., key=...))
-        for (int i = 1; i < nc; ++i) {
-          int8_t ck = cand[i]; double dk = cd[i];
-          int j = i - 1;
-          while (j >= 0 && cd[j] > dk) { cand[j + 1] = cand[j]; cd[j + 1] = cd[j]; --j; }
-          cand[j + 1] = ck; cd[j + 1] = dk;
-        }
-        int kids = bw < nc ? bw : nc;
-        for (int i = 0; i < kids; ++i) {
-          BeamItem& c = nq[nn++];
-          c.prio = it.prio + cd[i];
-          c.seen = it.seen | (1u << cand[i]);
-          for (int j = 0; j < level; ++j) c.path[j] = it.path[j];
-          c.path[level] = cand[i];
-        }
-      }
-      for (int i = 0; i < nn; ++i) q[i] = nq[i];
-      qn = nn;
-      (void)all;
-    }
-    // publish the path as a linked list over global pin indices
-    rs.start[net] = (uint16_t)(lo + start);
-    uint16_t prev = (uint16_t)(lo + start);
-    for (int j = 0; j < m; ++j) {
-      uint16_t g = gid[q[best_idx].path[j]];
-      rs.nxt[prev] = g;
-      prev = g;
-    }
-    rs.nxt[prev] = 0xFFFF;
   }
-  __syncwarp();
+  // points = net pins without the start (list.remove keeps the order)
+  int16_t x[kMaxBeamPoints + 1], y[kMaxBeamPoints + 1];
+  uint16_t gid[kMaxBeamPoints + 1];
+  uint64_t h[kMaxBeamPoints + 1];
+  int m = 0;
+  for (int i = 0; i < m_all; ++i) {
+    if (i == start) continue;
+    x[m] = pins[lo + i].x; y[m] = pins[lo + i].y; gid[m] = (uint16_t)(lo + i);
+    h[m] = py_tuple_hash(x[m], y[m]);
+    ++m;
+  }
+  const int sx = pins[lo + start].x, sy = pins[lo + start].y;
+  PyTab targets;
+  tab_clear(targets, 8);
+  for (int k = 0; k < m; ++k) tab_add(targets, k, h);
+
+  BeamItem q[kMaxBeamWidth * kMaxBeamWidth], nq[kMaxBeamWidth * kMaxBeamWidth];
+  int qn = 1;
+  q[0].prio = 0.0; q[0].seen = 0u;
+  int best_idx = 0;
+  for (int level = 0; level <= m; ++level) {  // level == number of visited points
+    // order the queue (selection of the min(bw, qn) smallest entries)
+    int order[kMaxBeamWidth];
+    int take = bw < qn ? bw : qn;
+    uint32_t used = 0;
+    for (int t = 0; t < take; ++t) {
+      int bi = -1;
+      for (int i = 0; i < qn; ++i) {
+        if ((used >> i) & 1u) continue;
+        if (bi < 0 || beam_less(q[i], q[bi], level, x, y)) bi = i;
+      }
+      used |= 1u << bi;
+      order[t] = bi;
+    }
+    if (level == m) { best_idx = order[0]; break; }  // first popped complete path wins
+    int nn = 0;
+    for (int t = 0; t < take; ++t) {
+      const BeamItem& it = q[order[t]];
+      const int hx = level ? x[it.path[level - 1]] : sx, hy = level ? y[it.path[level - 1]] : sy;
+      int8_t cand[kMaxBeamPoints + 1];
+      double cd[kMaxBeamPoints + 1];
+      int nc = tab_difference(targets, it.seen, h, cand);
+      for (int i = 0; i < nc; ++i)
+        cd[i] = norm2((double)(hx - x[cand[i]]), (double)(hy - y[cand[i]]), norm_fma);
+      // stable insertion sort by distance (sorted(..., key=...))
+      for (int i = 1; i < nc; ++i) {
+        int8_t ck = cand[i]; double dk = cd[i];
+        int j = i - 1;
+        while (j >= 0 && cd[j] > dk) { cand[j + 1] = cand[j]; cd[j + 1] = cd[j]; --j; }
+        cand[j + 1] = ck; cd[j + 1] = dk;
+      }
+      int kids = bw < nc ? bw : nc;
+      for (int i = 0; i < kids; ++i) {
+        BeamItem& c = nq[nn++];
+        c.prio = it.prio + cd[i];
+        c.seen = it.seen | (1u << cand[i]);
+        for (int j = 0; j < level; ++j) c.path[j] = it.path[j];
+        c.path[level] = cand[i];
+      }
+    }
+    for (int i = 0; i < nn; ++i) q[i] = nq[i];
+    qn = nn;
+  }
+  *start_out = (uint16_t)(lo + start);
+  uint16_t prev = (uint16_t)(lo + start);
+  for (int j = 0; j < m; ++j) {
+    uint16_t g = gid[q[best_idx].path[j]];
+    nxt[prev] = g;
+    prev = g;
+  }
+  nxt[prev] = 0xFFFF;
+}
+
+// Beam routes of all finished episodes of a step: ONE THREAD PER (job, net), so a warp
+// routes 32 independent nets (the router is serial per net).  The paths are written into
+// the job records; reward_kernel<true> picks them up.
+__global__ void __launch_bounds__(128) beam_kernel(const __grid_constant__ Params p) {
+  const Dims& d = p.d;
+  const int nets_max = d.K - 1;
+  const uint32_t count = p.job_count[p.step_no & 3];
+  const uint32_t total = count * (uint32_t)nets_max;
+  const int stride = job_stride(d.max_pins, d.K);
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const uint32_t j = idx / (uint32_t)nets_max;
+    const int net = (int)(idx - j * (uint32_t)nets_max);
+    uint8_t* job = p.jobs + (size_t)j * stride;
+    const RouteJob* hdr = reinterpret_cast<const RouteJob*>(job);
+    const int n_pins = hdr->n_pins;
+    if (net >= hdr->n_nets) continue;
+    const JobPin* pins = reinterpret_cast<const JobPin*>(job + 32);
+    int lo = 0;
+    while (lo < n_pins && pins[lo].net != net) ++lo;  // pins are net-major
+    int hi = lo;
+    while (hi < n_pins && pins[hi].net == net) ++hi;
+    uint16_t* nxt = reinterpret_cast<uint16_t*>(job + job_path_offset(d.max_pins));
+    uint16_t* start = nxt + d.max_pins;
+    beam_route_net(pins, lo, hi - lo, d.beam_width, d.norm_fma, nxt, start + net);
+  }
 }
 
 // crossings + wirelength of the beam route: segment headed by pin q = (q, nxt[q])

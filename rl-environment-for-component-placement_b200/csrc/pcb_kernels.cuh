@@ -1008,7 +1008,7 @@ __device__ __forceinline__ void finish_episode(const S& sh, const Params& p, Env
     uint32_t idx = 0;
     if (lane == 0) idx = atomicAdd(p.job_count + (p.step_no & 3), 1u);
     idx = __shfl_sync(kFull, idx, 0);
-    uint8_t* job = p.jobs + (size_t)idx * job_stride(sh.max_pins());
+    uint8_t* job = p.jobs + (size_t)idx * job_stride(sh.max_pins(), sh.K());
     if (lane == 0) {
       RouteJob j;
       j.env = (uint32_t)env; j.n_pins = (uint16_t)n_pins; j.n_nets = e.hdr->n_nets;
@@ -1252,7 +1252,7 @@ reward_kernel(const __grid_constant__ Params p) {
   const int scr_bytes = route_scratch_bytes(d.max_pins, d.K);
   RouteScratch rs = route_scratch(smem + (size_t)wic * ((scr_bytes + 15) & ~15), d.max_pins, d.K);
   for (uint32_t j = gw; j < count; j += nw) {
-    const uint8_t* job = p.jobs + (size_t)j * job_stride(d.max_pins);
+    const uint8_t* job = p.jobs + (size_t)j * job_stride(d.max_pins, d.K);
     const RouteJob hdr = *reinterpret_cast<const RouteJob*>(job);
     const int n_pins = hdr.n_pins, n_nets = hdr.n_nets, env = (int)hdr.env;
     route_prepare(reinterpret_cast<const JobPin*>(job + 32), rs, lane, n_pins, n_nets);
@@ -1261,7 +1261,11 @@ reward_kernel(const __grid_constant__ Params p) {
     if (!BEAM || d.reward_type == 0) {
       centroid_route(d, rs, lane, n_pins, crossings, length);
     } else if constexpr (BEAM) {
-      beam_paths(d, rs, lane, n_nets);
+      // the paths were routed by beam_kernel (one thread per net) into the job record
+      const uint16_t* jn = reinterpret_cast<const uint16_t*>(job + job_path_offset(d.max_pins));
+      for (int q = lane; q < n_pins; q += 32) rs.nxt[q] = jn[q];
+      for (int k = lane; k < n_nets; k += 32) rs.start[k] = jn[d.max_pins + k];
+      __syncwarp();
       beam_route(d, rs, lane, n_pins, n_nets, crossings, length);
       if (d.reward_type == 2) {  // "both": fewer crossings wins, beam on ties (pin:643-661)
         int c2; double l2;

@@ -142,7 +142,11 @@ struct __align__(16) RouteJob {
   double pad2;
 };
 struct JobPin { uint8_t x, y, net, pad; };
-PCB_HD constexpr int job_stride(int max_pins) { return 32 + align16c(max_pins * 4); }
+// job record: RouteJob (32 B) | JobPin[max_pins] | beam paths: nxt[max_pins] u16, start[K] u16
+PCB_HD constexpr int job_path_offset(int max_pins) { return 32 + align16c(max_pins * 4); }
+PCB_HD constexpr int job_stride(int max_pins, int K) {
+  return job_path_offset(max_pins) + align16c(max_pins * 2 + K * 2);
+}
 
 // Everything a kernel needs to know about the configuration; passed by value.
 struct Dims {
