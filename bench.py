@@ -180,8 +180,12 @@ def gpu_arm(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     N = args.envs
     cfg = CONFIGS[name]
-    env = pcbgpu.PcbVecEnv(cfg, N, device=local_rank, autoreset=True, obs_ring=OBS_RING,
+    # the observation ring must not fit in L2 (126 MB): small workloads get more slices
+    ring = max(OBS_RING, -(-300_000_000 // (N * ALGO_BYTES[name])))
+    env = pcbgpu.PcbVecEnv(cfg, N, device=local_rank, autoreset=True, obs_ring=ring,
                            bank_size=N * 4, seed=1000 + rank, generate_on_device=True)
+    if args.no_fused:
+        env.fused_rollout(False)
     seed = 7 + rank
     K, W = args.steps, args.warmup
     stream = torch.cuda.current_stream()
@@ -226,6 +230,10 @@ def gpu_arm(args, rank, world, local_rank):
     env.rollout_random(K, seed, actions_log=log)
     barrier()
     kt = env.kernel_times()
+    fz = env.fused_rollout_times()
+    fused = fz[1] > 0  # pin-less kinds: the whole rollout is one launch of rollout_small_kernel
+    if fused:
+        kt["step"] = (fz[0], fz[2])  # device time, step-equivalents
     stats2 = env.episode_stats(reset=True)
     # same again with the kernels strictly one after the other: the step kernel on its own
     prepare()
@@ -234,6 +242,9 @@ def gpu_arm(args, rank, world, local_rank):
     env.rollout_random(K, seed)
     barrier()
     kt_alone = env.kernel_times()
+    fz = env.fused_rollout_times()
+    if fused:
+        kt_alone["step"] = (fz[0], fz[2])
     env.reward_overlap(True)
     env.kernel_timing(False)
     env.episode_stats(reset=True)
@@ -306,8 +317,8 @@ def gpu_arm(args, rank, world, local_rank):
             "actions, sampled on device (Philox)", "autoreset": True,
             "instances": f"{N * 4} per GPU from the library's device generator (distribution of the reference's generate_instances)",
             "episode_phases": "staggered (1/%d of the envs finish every step)" % EP_LEN[name],
-            "l2": "working set larger than L2: every step writes a fresh %.0f MB observation slice "
-                  "(ring of %d slices)" % (N * (ALGO_BYTES[name]) / 1e6, OBS_RING),
+            "l2": "working set larger than L2: every step writes a fresh %.1f MB observation slice "
+                  "(ring of %d slices)" % (N * (ALGO_BYTES[name]) / 1e6, ring),
             "timing": "CUDA events on the launching stream around %d steps, max over ranks" % K,
         },
         "e2e": {"value": e2e_value, "unit": "env-steps/s",
@@ -317,7 +328,8 @@ def gpu_arm(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic, "kernel": "step_kernel",
+                     "frac": achieved / peak, "traffic": traffic,
+                     "kernel": "rollout_small_kernel (all steps in one launch; per step-equivalent)" if fused else "step_kernel",
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_env_step": ALGO_BYTES[name],
                      "envs_written_per_launch": written,
@@ -418,6 +430,8 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-fused", action="store_true",
+                    help="pin-less kinds: per-step launches instead of the multi-step rollout kernel")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

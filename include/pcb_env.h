@@ -211,6 +211,17 @@ int pcb_rollout_random(pcb_env_t* env, uint64_t seed, int n_steps, int32_t* d_ac
  * step t+1 (default on); 0 = strictly one after the other, as pcb_step always does. */
 int pcb_set_reward_overlap(pcb_env_t* env, int on);
 
+/* The pin-less kinds (square, rectangle; H, W <= 32) run pcb_rollout_random as ONE launch
+ * of a multi-step kernel that keeps the state on chip and packs 32/LPE environments into a
+ * warp (LPE = 8, 16, 32 lanes >= H) -- default on; the result is bit-identical to n_steps x
+ * { pcb_sample_random_actions; pcb_step }.  pcb_set_fused_rollout(env, 0) selects the
+ * per-step launches instead; returns 1 when the fused kernel will be used, 0 when not
+ * (pin kinds, boards wider than 32), negative on error.  pcb_fused_rollout_times: device
+ * time [ms], launches and steps of the fused kernel since the last call (needs
+ * pcb_enable_kernel_timing). */
+int pcb_set_fused_rollout(pcb_env_t* env, int on);
+int pcb_fused_rollout_times(pcb_env_t* env, double* ms, int64_t* launches, int64_t* steps);
+
 /* Measurement aid: when on, every kernel launch is bracketed by CUDA events on the
  * launching stream.  pcb_kernel_times waits for them and returns the summed device
  * time [ms] and launch count per kernel {step, reward, reset, sample}, then clears. */

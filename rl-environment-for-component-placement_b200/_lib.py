@@ -13,7 +13,8 @@ SYMBOLS = (
     "pcb_current_slice", "pcb_episode_stats", "pcb_get_occupancy", "pcb_launch_count",
     "pcb_last_error", "pcb_abi_version", "pcb_rollout_random", "pcb_enable_kernel_timing",
     "pcb_kernel_times", "pcb_current_result_half", "pcb_generate_host", "pcb_generate_instances_device", "pcb_state_layout", "pcb_get_state",
-    "pcb_set_state", "pcb_set_reward_overlap", "pcb_shape_id",
+    "pcb_set_state", "pcb_set_reward_overlap", "pcb_shape_id", "pcb_set_fused_rollout",
+    "pcb_fused_rollout_times",
 )
 
 
@@ -85,6 +86,9 @@ def load(path=None):
     lib.pcb_rollout_random.argtypes = [vp, u64, i32, vp, vp]
     lib.pcb_enable_kernel_timing.argtypes = [vp, i32]
     lib.pcb_set_reward_overlap.argtypes = [vp, i32]
+    lib.pcb_set_fused_rollout.argtypes = [vp, i32]
+    lib.pcb_fused_rollout_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64),
+                                            ctypes.POINTER(i64)]
     lib.pcb_kernel_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
     lib.pcb_last_error.restype = ctypes.c_char_p
     lib.pcb_abi_version.restype = i32

@@ -20,6 +20,7 @@
 #include "pcb_gen.h"
 #include "pcb_gen_device.cuh"
 #include "pcb_kernels.cuh"
+#include "pcb_small.cuh"
 
 using namespace pcb;
 
@@ -86,6 +87,10 @@ struct pcb_env {
   cudaEvent_t ev_step[2], ev_rew[2];
   bool rew_pending[2];
   bool overlap;          // pcb_rollout_random overlaps the reward kernel with the next step
+  bool fused;            // pcb_rollout_random uses rollout_small_kernel (pin-less kinds, H, W <= 32)
+  size_t small_smem;     // its dynamic shared memory per CTA
+  double fused_ms;       // timing (pcb_enable_kernel_timing): device time, launches, env-steps
+  int64_t fused_launches, fused_steps;
   std::vector<TensorDesc> tensors;
   std::vector<void*> allocs;
   // optional per-kernel CUDA-event timing (pcb_enable_kernel_timing)
@@ -246,6 +251,37 @@ int launch(pcb_env* e, KernelId id, const Params& p, cudaStream_t st, int reward
   }
   e->launches += 1;
   return 0;
+}
+
+// rollout_small_kernel: instantiations and dispatch.  LPE (lanes per env) follows from H.
+template <typename S, int LPE>
+int small_launch(bool configure, size_t sm, dim3 grid, dim3 block, cudaStream_t st, const RolloutParams& p) {
+  if (configure) return set_smem(rollout_small_kernel<LPE, S>, sm);
+  rollout_small_kernel<LPE, S><<<grid, block, sm, st>>>(p);
+  return 0;
+}
+
+int small_dispatch(pcb_env* e, bool configure, cudaStream_t st, const RolloutParams& p) {
+  const int lpe = small_lanes_per_env(e->d.H);
+  const int per_cta = kWarpsPerCta * (32 / lpe);
+  dim3 grid((e->n_envs + per_cta - 1) / per_cta), block(kWarpsPerCta * 32);
+  const size_t sm = e->small_smem;
+  switch (e->shape_id) {
+    case 1: return small_launch<ShapeB, 16>(configure, sm, grid, block, st, p);
+    case 7: return small_launch<ShapeRefRect, 16>(configure, sm, grid, block, st, p);
+    case 8: return small_launch<ShapeRefSquare, 16>(configure, sm, grid, block, st, p);
+    case 9: return small_launch<ShapeA, 8>(configure, sm, grid, block, st, p);
+#ifdef PCB_USER_SHAPE
+    case 100:
+      if constexpr (kUserDims[0] <= 1 && !kUserWide)
+        return small_launch<ShapeUser, small_lanes_per_env(kUserDims[1])>(configure, sm, grid, block, st, p);
+      break;
+#endif
+    default: break;
+  }
+  if (lpe == 8) return small_launch<DynShape, 8>(configure, sm, grid, block, st, p);
+  if (lpe == 16) return small_launch<DynShape, 16>(configure, sm, grid, block, st, p);
+  return small_launch<DynShape, 32>(configure, sm, grid, block, st, p);
 }
 
 template <typename P>
@@ -461,6 +497,15 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
     default:
       if (e->wide) TRY((set_smem_shape<2, uint64_t, DynShape>(e->smem_bytes)));
       else TRY((set_smem_shape<1, uint32_t, DynShape>(e->smem_bytes)));
+  }
+  e->fused = d.kind <= 1 && !e->wide;
+  e->small_smem = 0; e->fused_ms = 0.0; e->fused_launches = 0; e->fused_steps = 0;
+  if (e->fused) {
+    const int per_cta = kWarpsPerCta * (32 / small_lanes_per_env(d.H));
+    e->small_smem = (size_t)kLutBytes + (size_t)small_env_smem(d.C, d.H * d.W) * per_cta;
+    RolloutParams none;
+    memset(&none, 0, sizeof none);
+    TRY(small_dispatch(e, true, nullptr, none));
   }
   e->jobs = nullptr; e->job_count = nullptr; e->reward_smem = 0; e->reward_grid = 1; e->reward_grid_side = 1;
   e->side = nullptr; e->rew_pending[0] = e->rew_pending[1] = false; e->overlap = PCB_OVERLAP_REWARD != 0;
@@ -865,11 +910,47 @@ int pcb_set_state(pcb_env_t* e, const void* h_state, uint64_t step_no, void* str
 
 int64_t pcb_launch_count(pcb_env_t* e) { return e ? e->launches : 0; }
 
+// the pin-less kinds: all n_steps in one launch of rollout_small_kernel (pcb_small.cuh)
+static int rollout_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_actions_log, cudaStream_t st) {
+  CU(cudaSetDevice(e->device));
+  RolloutParams p;
+  memset(&p, 0, sizeof p);
+  p.d = e->d;
+  p.base = e->base;
+  p.state = e->state; p.bank = e->bank; p.ratio_lut = e->ratio_lut; p.stats = e->stats;
+  p.actions_log = d_actions_log;
+  p.seed = seed; p.step_no = e->step_no; p.bank_count = e->bank_count;
+  p.n_envs = e->n_envs; p.n_steps = n_steps; p.ring = e->ring; p.slice0 = e->slice;
+  cudaEvent_t a = nullptr, b = nullptr;
+  if (e->timing) {
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    CU(cudaEventRecord(a, st));
+  }
+  int rc = small_dispatch(e, false, st, p);
+  if (rc) return rc;
+  CU(cudaGetLastError());
+  if (e->timing) {
+    CU(cudaEventRecord(b, st));
+    CU(cudaEventSynchronize(b));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    e->fused_ms += ms; e->fused_launches += 1; e->fused_steps += n_steps;
+  }
+  e->launches += 1;
+  e->slice = (e->slice + n_steps) % e->ring;
+  e->step_no += (uint64_t)n_steps;
+  return 0;
+}
+
 int pcb_rollout_random(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_actions_log, void* stream) {
   int rc = ready(e);
   if (rc) return rc;
   if (n_steps < 0) return fail(PCB_ERR_INVALID, "n_steps must be >= 0");
   if (n_steps == 0) return 0;
+  if (e->fused) return rollout_fused(e, seed, n_steps, d_actions_log, (cudaStream_t)stream);
   const size_t per = (size_t)e->n_envs * (e->d.kind == 0 ? 2 : 3);
   // the first action comes from the stand-alone sampler; every step kernel then also
   // draws the action of the following step (same Philox counter as the sampler would use)
@@ -891,6 +972,19 @@ int pcb_rollout_random(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_acti
 int pcb_set_reward_overlap(pcb_env_t* e, int on) {
   if (!e) return fail(PCB_ERR_INVALID, "env is NULL");
   e->overlap = on != 0;
+  return 0;
+}
+
+int pcb_set_fused_rollout(pcb_env_t* e, int on) {
+  if (!e) return fail(PCB_ERR_INVALID, "env is NULL");
+  e->fused = on != 0 && e->d.kind <= 1 && !e->wide;
+  return e->fused ? 1 : 0;
+}
+
+int pcb_fused_rollout_times(pcb_env_t* e, double* ms, int64_t* launches, int64_t* steps) {
+  if (!e || !ms || !launches || !steps) return fail(PCB_ERR_INVALID, "NULL argument");
+  *ms = e->fused_ms; *launches = e->fused_launches; *steps = e->fused_steps;
+  e->fused_ms = 0.0; e->fused_launches = 0; e->fused_steps = 0;
   return 0;
 }
 

@@ -172,6 +172,18 @@ class PcbVecEnv:
         """rollout_random: run the reward kernel of step t alongside the step kernel of t+1."""
         self._check(self.lib.pcb_set_reward_overlap(self._h, 1 if on else 0))
 
+    def fused_rollout(self, on):
+        """Pin-less kinds: rollout_random as one multi-step launch (default) or per-step
+        launches.  Returns True when the fused kernel will be used."""
+        return bool(self._check(self.lib.pcb_set_fused_rollout(self._h, 1 if on else 0)))
+
+    def fused_rollout_times(self):
+        """(ms, launches, steps) of the fused rollout kernel since the last call."""
+        ms, n, k = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
+        self._check(self.lib.pcb_fused_rollout_times(self._h, ctypes.byref(ms), ctypes.byref(n),
+                                                    ctypes.byref(k)))
+        return ms.value, int(n.value), int(k.value)
+
     def kernel_timing(self, on):
         self._check(self.lib.pcb_enable_kernel_timing(self._h, 1 if on else 0))
 

@@ -76,6 +76,92 @@ def test_fused_rollout_equals_sample_then_step(name):
     a.close(); b.close()
 
 
+SMALL = ["A", "A2", "B", "S_sq", "S_rect", "S_rect_full", "REF_rect", "REF_square"]
+
+
+@pytest.mark.parametrize("autoreset", [True, False])
+@pytest.mark.parametrize("name", SMALL)
+def test_fused_small_rollout_is_bit_identical_to_per_step_launches(name, autoreset):
+    """rollout_small_kernel (all steps in one launch, 32/LPE envs per warp) against the
+    per-step launches: actions, every ring slice, results, state records, statistics."""
+    n, R = 777, 4  # 777: the last warp / CTA is partly empty
+    a = make(name, n, seed=3, autoreset=autoreset, obs_ring=R)
+    b = make(name, n, seed=3, autoreset=autoreset, obs_ring=R)
+    assert a.fused_rollout(True) and not b.fused_rollout(False)
+    a.reset(); b.reset()
+    w = a.spec.action_width
+    for chunk in (1, 6, 23):  # several calls: the ring wraps, the step counter carries over
+        la = torch.zeros((chunk, n, w), dtype=torch.int32, device="cuda")
+        lb = torch.zeros_like(la)
+        a.rollout_random(chunk, seed=9, actions_log=la)
+        b.rollout_random(chunk, seed=9, actions_log=lb)
+        torch.cuda.synchronize()
+        assert torch.equal(la, lb), (name, chunk, "actions")
+        assert a.lib.pcb_current_slice(a._h) == b.lib.pcb_current_slice(b._h)
+        for k in a.obs_ring_tensors:
+            assert torch.equal(a.obs_ring_tensors[k], b.obs_ring_tensors[k]), (name, chunk, k)
+        for k in a._res:
+            assert torch.equal(a._res[k], b._res[k]), (name, chunk, k)
+        sa, sb = a.state_dict(), b.state_dict()
+        assert sa["step_no"] == sb["step_no"] and np.array_equal(sa["state"], sb["state"])
+    sa, sb = a.episode_stats(), b.episode_stats()
+    assert sa["episodes"] == sb["episodes"] and sa["sum_length"] == sb["sum_length"]
+    assert sa["sum_return"] == sb["sum_return"]  # integer-valued float64 sums: exact
+    if autoreset:
+        assert sa["episodes"] > 0
+    # the fused kernel is one launch per call
+    l0 = a.launch_count
+    a.rollout_random(17, seed=1)
+    assert a.launch_count == l0 + 1
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("name", ["A", "B", "S_rect", "S_sq", "REF_rect"])
+def test_fused_small_rollout_against_the_oracle(name):
+    """The logged actions of a fused rollout replayed through the oracle: every
+    observation of every step (ring of T+1 slices) must be the oracle's."""
+    from parity import compare_obs
+    from ref_harness import make_oracle
+
+    cfg = CONFIGS[name]
+    square = cfg["type"] == "square"
+    N, T, episodes = 24, 30, 12
+    insts = None if square else [draw_instance(cfg, s + k * 100003) for k in range(episodes)
+                                 for s in range(N)]
+    env = make(name, N, autoreset=True, instances=insts, obs_ring=T + 1)
+    assert env.fused_rollout(True)
+    env.reset()
+    log = torch.zeros((T, N, env.spec.action_width), dtype=torch.int32, device="cuda")
+    env.rollout_random(T, seed=5, actions_log=log)
+    torch.cuda.synchronize()
+    acts = log.cpu().numpy()
+    ring = env.obs_ring_tensors
+    C = env.spec.max_num_components
+    n_done = 0
+    for i in range(N):
+        o = make_oracle(cfg)
+        o.reset() if square else o.reset(instance=insts[i])
+        epi = 0
+        for t in range(T):
+            ro, rr, rd, _ = o.step(tuple(int(v) for v in acts[t, i]))
+            assert rr == 1.0, (name, i, t, "the random policy only picks valid actions")
+            if rd:
+                epi += 1
+                n_done += 1
+                ro = o.reset() if square else o.reset(instance=insts[(epi * N + i) % len(insts)])
+            compare_obs({k: v[t + 1] for k, v in ring.items()}, i, ro, C, (name, i, t))
+    st = env.episode_stats()
+    assert st["episodes"] == n_done > 0
+    env.close()
+
+
+def test_fused_rollout_is_refused_for_pin_kinds_and_wide_boards():
+    for name in ("C", "S_wide_sq", "S_wide_rect"):
+        env = make(name, 8)
+        assert not env.fused_rollout(True)
+        env.close()
+
+
 def test_step_host_and_flat_actions_match_device_step():
     import pcbgpu
 
