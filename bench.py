@@ -34,8 +34,11 @@ OBS_RING = 4
 ALGO_BYTES = {"A": 161, "B": 1049, "C": 7699, "D": 15775, "E": 28821,
               # the reference's shipped 10x10 pin config (agent/config/rectangle_pin_model.json):
               # grid 100 + mask 400 + features 100 + placement 5 + pins 160 + 40 + 21 + 2 * 192 state
-              "REF_pin": 1210, "C_both": 7699, "C_beam": 7699}
-EP_LEN = {"A": 4, "B": 6, "C": 10, "D": 10, "E": 32, "REF_pin": 5, "C_both": 10, "C_beam": 10}
+              "REF_pin": 1210, "C_both": 7699, "C_beam": 7699,
+              # rectangle_model.json: grid 100 + mask 200 + features 400 + masks 40 + 21 + 2 * 240 state
+              "REF_rect": 1241}
+EP_LEN = {"A": 4, "B": 6, "C": 10, "D": 10, "E": 32, "REF_pin": 5, "C_both": 10, "C_beam": 10,
+          "REF_rect": 8}
 WORKLOAD_DESC = {
     "A": "A: dummy_env_square 8x8, 3x3 components",
     "B": "B: dummy_env_rectangular 16x16, 6 rectangular components",
@@ -44,6 +47,7 @@ WORKLOAD_DESC = {
     "E": "E: dummy_env_rectangular_pin 64x64, 32 components, 16 nets, centroid reward",
     "C_both": "C_both: as C with reward_type='both' (beam-search route + centroid route)",
     "C_beam": "C_beam: as C with reward_type='beam'",
+    "REF_rect": "REF_rect: dummy_env_rectangular 10x10, 20 components 2..4 (agent/config/rectangle_model.json)",
     "REF_pin": "REF_pin: dummy_env_rectangular_pin 10x10, 5 components 2x2, 3 nets x 6 pins (agent/config/rectangle_pin_model.json)",
 }
 

@@ -87,6 +87,7 @@ struct pcb_env {
   cudaEvent_t ev_step[2], ev_rew[2];
   bool rew_pending[2];
   bool overlap;          // pcb_rollout_random overlaps the reward kernel with the next step
+  int sms;               // multiprocessors of the device
   bool fused;            // pcb_rollout_random uses rollout_small_kernel (pin-less kinds, H, W <= 32)
   size_t small_smem;     // its dynamic shared memory per CTA
   double fused_ms;       // timing (pcb_enable_kernel_timing): device time, launches, env-steps
@@ -262,10 +263,13 @@ int small_launch(bool configure, size_t sm, dim3 grid, dim3 block, cudaStream_t 
 }
 
 int small_dispatch(pcb_env* e, bool configure, cudaStream_t st, const RolloutParams& p) {
-  const int lpe = small_lanes_per_env(e->d.H);
-  const int per_cta = kWarpsPerCta * (32 / lpe);
-  dim3 grid((e->n_envs + per_cta - 1) / per_cta), block(kWarpsPerCta * 32);
-  const size_t sm = e->small_smem;
+  const int lpe = small_lanes_per_env(e->d.H), G = 32 / lpe;
+  // few envs: one-warp CTAs spread evenly over the SMs (all resident at once); many: 4 warps
+  const int warps = (e->n_envs + G - 1) / G;
+  const int wpc = warps <= e->sms * 32 ? 1 : kWarpsPerCta;
+  dim3 grid((warps + wpc - 1) / wpc), block(wpc * 32);
+  const size_t sm = configure ? e->small_smem
+                              : (size_t)kLutBytes + (size_t)small_env_smem(e->d.C, e->d.H * e->d.W) * wpc * G;
   switch (e->shape_id) {
     case 1: return small_launch<ShapeB, 16>(configure, sm, grid, block, st, p);
     case 7: return small_launch<ShapeRefRect, 16>(configure, sm, grid, block, st, p);
@@ -499,6 +503,8 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
       else TRY((set_smem_shape<1, uint32_t, DynShape>(e->smem_bytes)));
   }
   e->fused = d.kind <= 1 && !e->wide;
+  e->sms = 148;
+  cudaDeviceGetAttribute(&e->sms, cudaDevAttrMultiProcessorCount, device);
   e->small_smem = 0; e->fused_ms = 0.0; e->fused_launches = 0; e->fused_steps = 0;
   if (e->fused) {
     const int per_cta = kWarpsPerCta * (32 / small_lanes_per_env(d.H));

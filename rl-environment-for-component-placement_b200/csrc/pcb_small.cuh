@@ -8,7 +8,7 @@
 // at small batches (4 096 envs: 6.5 us per step against 0.7 us of HBM time) and a full
 // warp per env leaves half (16x16) or three quarters (8x8) of the lanes idle.  Here
 //   * LPE lanes own one environment (LPE = 8, 16 or 32 >= H, lane = grid row), so a warp
-//     steps 32/LPE environments; every shuffle / vote is confined to the group's lane mask,
+//     steps 32/LPE environments; the groups of a warp run converged and differ by predicates,
 //   * the state lives in registers (board row, counters) and shared memory (components)
 //     for all n_steps; HBM sees it once at the start and once at the end,
 //   * the next instance of an env is prefetched from the bank at the start of an episode,
@@ -45,59 +45,80 @@ PCB_HD constexpr int small_env_smem(int C, int HW) {
 
 PCB_HD constexpr int small_lanes_per_env(int H) { return H <= 8 ? 8 : (H <= 16 ? 16 : 32); }
 
+// Every shuffle / vote below is issued by the WHOLE warp with the full mask (a group mask
+// that is not a compile-time constant costs a MATCH + divergence check per operation:
+// measured, half of the kernel's instructions), so the control flow around them is kept
+// warp-uniform and the groups only differ by predicates.  Shuffles are confined to the
+// group by their width, votes by masking the ballot.
 template <int LPE>
-__device__ __forceinline__ uint32_t rows_ahead_g(uint32_t v, int dlt, int sl, unsigned gmask) {
-  const uint32_t t = __shfl_down_sync(gmask, v, dlt, LPE);
+__device__ __forceinline__ bool group_any(bool pred, unsigned gmask) {
+  return (__ballot_sync(kFull, pred) & gmask) != 0u;
+}
+
+template <int LPE>
+__device__ __forceinline__ uint32_t rows_ahead_g(uint32_t v, int dlt, int sl) {
+  const uint32_t t = __shfl_down_sync(kFull, v, dlt, LPE);
   return sl + dlt < LPE ? t : 0u;
 }
 
-// footprint_mask (pcb_kernels.cuh) for one row per lane inside an LPE-lane group; branch-free
-// for the usual component sizes so that the groups of a warp stay converged
+// footprint_mask (pcb_kernels.cuh) for one row per lane inside an LPE-lane group.
+// small = every footprint of the configuration is at most 4x4 (warp-uniform).
 template <int LPE>
 __device__ __forceinline__ uint32_t footprint_mask_g(uint32_t occ, int ph, int pw, int H, int W,
-                                                     int sl, unsigned gmask) {
+                                                     int sl, bool small, int pmax) {
   uint32_t v = sl < H ? (~occ & low_mask<uint32_t>(W)) : 0u;
-  if (ph <= 4 && pw <= 4) {
+  if (small) {
     const uint32_t a = v & (v >> 1);
     uint32_t r = pw >= 2 ? a : v;
     if (pw == 3) r = a & (v >> 2);
     if (pw == 4) r = a & (a >> 2);
     v = r;
-    const uint32_t t1 = rows_ahead_g<LPE>(v, 1, sl, gmask);
+    const uint32_t t1 = rows_ahead_g<LPE>(v, 1, sl);
     uint32_t b = ph >= 2 ? (v & t1) : v;
-    const uint32_t t2 = rows_ahead_g<LPE>(ph == 4 ? b : v, 2, sl, gmask);
+    const uint32_t t2 = rows_ahead_g<LPE>(ph == 4 ? b : v, 2, sl);
     if (ph >= 3) b &= t2;
     return b;
   }
-  int s = 1;
-  while (2 * s <= pw) { v &= v >> s; s <<= 1; }
-  if (s < pw) v &= v >> (pw - s);
-  s = 1;
-  while (2 * s <= ph) { v &= rows_ahead_g<LPE>(v, s, sl, gmask); s <<= 1; }
-  if (s < ph) v &= rows_ahead_g<LPE>(v, ph - s, sl, gmask);
-  return v;
+  // any size: the trip counts follow the configuration, the footprint only predicates
+  uint32_t acc = v;
+  for (int k = 1; k < pmax; ++k)
+    if (k < pw) acc &= v >> k;
+  v = acc;
+  for (int k = 1; k < pmax; ++k) {
+    const uint32_t t = rows_ahead_g<LPE>(v, k, sl);
+    if (k < ph) acc &= t;
+  }
+  return acc;
 }
 
-// sample_action (pcb_kernels.cuh) inside a group: same counters, same draw
+// sample_action (pcb_kernels.cuh) for every group of the warp at once: same counters, same
+// draw.  have = the group has at least one valid action.
 template <int LPE, typename S>
-__device__ __forceinline__ void sample_action_g(const S& sh, uint32_t m0, uint32_t m1, uint64_t seed,
-                                                int env, uint64_t step_no, int lane, unsigned gmask,
+__device__ __forceinline__ void sample_action_g(const S& sh, uint32_t m0, uint32_t m1, bool have,
+                                                uint64_t seed, int env, uint64_t step_no, int lane,
                                                 int& ao, int& ax, int& ay) {
   ao = 0; ax = 0; ay = 0;
-  if (__any_sync(gmask, (m0 | m1) != 0u)) {
-    const int H = sh.H(), W = sh.W();
-    for (int t = 0; t < PCB_SAMPLE_TRIES; ++t) {
-      const uint64_t r = action_rand64(seed + 0x632BE59BD9B4E019ull * (uint64_t)(t + 1), (uint32_t)env, step_no);
-      const int o = (int)((((uint32_t)r & 0x1fffffu) * (uint32_t)sh.O()) >> 21);
-      const int row = (int)((((uint32_t)(r >> 21) & 0x1fffffu) * (uint32_t)H) >> 21);
-      const int col = (int)((((uint32_t)(r >> 42) & 0x1fffffu) * (uint32_t)W) >> 21);
-      const uint32_t bits = __shfl_sync(gmask, (o & 1) ? m1 : m0, row, LPE);
-      if ((bits >> col) & 1u) { ao = o; ax = row; ay = col; return; }  // group-uniform
-    }
+  const int H = sh.H(), W = sh.W();
+  bool open = have;  // still looking for an accepted cell
+  for (int t = 0; t < PCB_SAMPLE_TRIES; ++t) {
+    if (!__any_sync(kFull, open)) break;
+    const uint64_t r = action_rand64(seed + 0x632BE59BD9B4E019ull * (uint64_t)(t + 1), (uint32_t)env, step_no);
+    const int o = (int)((((uint32_t)r & 0x1fffffu) * (uint32_t)sh.O()) >> 21);
+    const int row = (int)((((uint32_t)(r >> 21) & 0x1fffffu) * (uint32_t)H) >> 21);
+    const int col = (int)((((uint32_t)(r >> 42) & 0x1fffffu) * (uint32_t)W) >> 21);
+    const uint32_t bits = __shfl_sync(kFull, (o & 1) ? m1 : m0, row, LPE);
+    if (open && ((bits >> col) & 1u)) { ao = o; ax = row; ay = col; open = false; }
   }
-  const int tot0 = __reduce_add_sync(gmask, __popc(m0)), tot1 = __reduce_add_sync(gmask, __popc(m1));
+  if (!__any_sync(kFull, open)) return;
+  // exact method for the groups that are still open: k-th set bit in np.argwhere order
+  const int sl = lane & (LPE - 1);
+  int tot0 = __popc(m0), tot1 = __popc(m1);
+#pragma unroll
+  for (int off = 1; off < LPE; off <<= 1) {
+    tot0 += __shfl_xor_sync(kFull, tot0, off, LPE);
+    tot1 += __shfl_xor_sync(kFull, tot1, off, LPE);
+  }
   const int total = sh.O() == 2 ? tot0 + tot1 : tot0;
-  if (total <= 0) return;
   const uint32_t r = action_rand(seed, (uint32_t)env, step_no);
   int kth = (int)__umulhi(r, (uint32_t)total);
   const bool second = kth >= tot0;
@@ -105,32 +126,29 @@ __device__ __forceinline__ void sample_action_g(const S& sh, uint32_t m0, uint32
   const uint32_t bits = second ? m1 : m0;
   const int c = __popc(bits);
   int incl = c;
-  const int sl = lane & (LPE - 1);
 #pragma unroll
   for (int off = 1; off < LPE; off <<= 1) {
-    const int v = __shfl_up_sync(gmask, incl, off, LPE);
+    const int v = __shfl_up_sync(kFull, incl, off, LPE);
     if (sl >= off) incl += v;
   }
   const int excl = incl - c;
-  const unsigned who = __ballot_sync(gmask, kth >= excl && kth < incl);
-  const int col = nth_bit32(bits, kth - excl);
-  const int src = __ffs(who) - 1;  // absolute lane of the row that holds the kth bit
-  ay = __shfl_sync(gmask, col, src);
-  ax = src & (LPE - 1);
-  ao = second ? 1 : 0;
+  const unsigned who = __ballot_sync(kFull, kth >= excl && kth < incl) >> (lane & ~(LPE - 1));
+  const int src = (__ffs(who) - 1) & (LPE - 1);  // row that holds the kth bit
+  const int col = __shfl_sync(kFull, nth_bit32(bits, kth - excl), src, LPE);
+  if (open && total > 0) { ao = second ? 1 : 0; ax = src; ay = col; }
 }
 
 // one board (bit row per lane) -> H*W bytes of 0/1
 template <int LPE, typename S>
 __device__ __forceinline__ void write_board_g(const S& sh, uint8_t* dst, uint32_t bits, uint32_t* flat,
-                                              int sl, unsigned gmask, const uint2* lut) {
+                                              int sl, bool live, const uint2* lut) {
   const int H = sh.H(), W = sh.W();
   if (W == 16) {
-    if (sl < H) st_stream(reinterpret_cast<uint4*>(dst) + sl, expand16(lut, bits));
+    if (live && sl < H) st_stream(reinterpret_cast<uint4*>(dst) + sl, expand16(lut, bits));
   } else if (W == 8) {
-    if (sl < H) st_stream(reinterpret_cast<uint2*>(dst) + sl, lut[bits & 0xffu]);
+    if (live && sl < H) st_stream(reinterpret_cast<uint2*>(dst) + sl, lut[bits & 0xffu]);
   } else if (W == 32) {
-    if (sl < H) {
+    if (live && sl < H) {
       st_stream(reinterpret_cast<uint4*>(dst) + 2 * sl, expand16(lut, bits));
       st_stream(reinterpret_cast<uint4*>(dst) + 2 * sl + 1, expand16(lut, bits >> 16));
     }
@@ -138,24 +156,26 @@ __device__ __forceinline__ void write_board_g(const S& sh, uint8_t* dst, uint32_
     // dense bit string (bit row*W + col) in shared memory, then 16 / 4 / 1 bits per lane
     const int nbits = H * W, nwords = (nbits + 31) >> 5;
     for (int i = sl; i < nwords + 1; i += LPE) flat[i] = 0u;
-    __syncwarp(gmask);
+    __syncwarp();
     if (sl < H && bits) {
       const int pos = sl * W, lo = pos >> 5;
       const uint64_t a = (uint64_t)bits << (pos & 31);
       atomicOr(flat + lo, (uint32_t)a);
       if (a >> 32) atomicOr(flat + lo + 1, (uint32_t)(a >> 32));
     }
-    __syncwarp(gmask);
-    if ((nbits & 15) == 0) {
-      for (int q = sl; q < (nbits >> 4); q += LPE)
-        st_stream(reinterpret_cast<uint4*>(dst) + q, expand16(lut, flat[q >> 1] >> (16 * (q & 1))));
-    } else if ((nbits & 3) == 0) {
-      for (int q = sl; q < (nbits >> 2); q += LPE)
-        st_stream(reinterpret_cast<uint32_t*>(dst) + q, spread4((flat[q >> 3] >> (4 * (q & 7))) & 15u));
-    } else {
-      for (int b = sl; b < nbits; b += LPE) st_stream(dst + b, (uint8_t)((flat[b >> 5] >> (b & 31)) & 1u));
+    __syncwarp();
+    if (live) {
+      if ((nbits & 15) == 0) {
+        for (int q = sl; q < (nbits >> 4); q += LPE)
+          st_stream(reinterpret_cast<uint4*>(dst) + q, expand16(lut, flat[q >> 1] >> (16 * (q & 1))));
+      } else if ((nbits & 3) == 0) {
+        for (int q = sl; q < (nbits >> 2); q += LPE)
+          st_stream(reinterpret_cast<uint32_t*>(dst) + q, spread4((flat[q >> 3] >> (4 * (q & 7))) & 15u));
+      } else {
+        for (int b = sl; b < nbits; b += LPE) st_stream(dst + b, (uint8_t)((flat[b >> 5] >> (b & 31)) & 1u));
+      }
     }
-    __syncwarp(gmask);
+    __syncwarp();
   }
 }
 
@@ -170,15 +190,21 @@ rollout_small_kernel(const __grid_constant__ RolloutParams p) {
   const int sl = lane & (LPE - 1), eic = wic * G + lane / LPE;
   unsigned gmask = kFull;
   if constexpr (LPE < 32) gmask = ((1u << LPE) - 1u) << (lane & ~(LPE - 1));
-  const int env = blockIdx.x * (kWarpsPerCta * G) + eic;
+  const int env_raw = blockIdx.x * ((int)(blockDim.x >> 5) * G) + eic;
   build_expand_lut(smem);
-  if (env >= p.n_envs) return;  // whole groups leave; the rest only uses group-masked syncs
+  // a group past the last env keeps running on env 0's data with every store switched off,
+  // so that the warp stays converged
+  const bool live = env_raw < p.n_envs;
+  if (!__any_sync(kFull, live)) return;
+  const int env = live ? env_raw : 0;
   const uint2* lut = reinterpret_cast<const uint2*>(smem);
   const int kind = sh.kind(), H = sh.H(), W = sh.W(), C = sh.C(), HW = H * W, O = sh.O();
   uint32_t* comps = reinterpret_cast<uint32_t*>(smem + kLutBytes + (size_t)eic * small_env_smem(C, HW));
   uint32_t* flat = comps + (align16c(C * 4) >> 2);
-  const size_t N = (size_t)p.n_envs;
+  const uint32_t N = (uint32_t)p.n_envs;
   const int aw = kind == 0 ? 2 : 3;
+  const int pmax = kind == 0 ? d.sq_n : (d.mh > d.mw ? d.mh : d.mw);
+  const bool small = pmax <= 4;
 
   // ---- state: HBM -> registers / shared memory (once) ----
   uint8_t* gs = p.state + (size_t)env * sh.st_stride();
@@ -196,14 +222,13 @@ rollout_small_kernel(const __grid_constant__ RolloutParams p) {
   }
   for (int c = sl; c < C; c += LPE) comps[c] = reinterpret_cast<const uint32_t*>(gs + sh.st_comps())[c];
   uint32_t occ = reinterpret_cast<const uint32_t*>(gs + sh.st_occ())[sl];
-  __syncwarp(gmask);
+  __syncwarp();
 
   // next instance of this env, fetched long before the episode ends
   constexpr int kPre = 2;  // components per lane kept in registers: C <= kPre * LPE, else re-read
   uint32_t nxt_hdr = 1u, nxt_comp[kPre] = {0u, 0u};
   auto prefetch = [&](uint32_t cur_slot) {
-    if (kind == 0) return;
-    uint32_t s2 = cur_slot + (uint32_t)p.n_envs;
+    uint32_t s2 = cur_slot + N;
     if (p.bank_count) s2 %= p.bank_count;
     const uint8_t* rec = p.bank + (size_t)s2 * sh.rec_stride();
     nxt_hdr = *reinterpret_cast<const uint32_t*>(rec);
@@ -211,68 +236,63 @@ rollout_small_kernel(const __grid_constant__ RolloutParams p) {
     for (int k = 0; k < kPre; ++k)
       if (sl + k * LPE < C) nxt_comp[k] = reinterpret_cast<const uint32_t*>(rec + sh.rec_comps())[sl + k * LPE];
   };
-  prefetch(slot);
+  if (kind != 0) prefetch(slot);
 
-  auto masks = [&](uint32_t& m0, uint32_t& m1) {
-    m0 = 0u; m1 = 0u;
+  uint32_t m0, m1;
+  auto masks = [&]() {  // warp-uniform: called by all lanes; returns "the group has a valid action"
     if (kind == 0) {
-      m0 = footprint_mask_g<LPE>(occ, d.sq_n, d.sq_n, H, W, sl, gmask);
+      m0 = footprint_mask_g<LPE>(occ, d.sq_n, d.sq_n, H, W, sl, small, pmax);
+      m1 = 0u;
     } else {
-      const bool have = cur < n_comp;  // group-uniform
+      const bool have = cur < n_comp;
       const uint32_t r = comps[have ? cur : 0];
       const int ch = r & 0xff, cw = (r >> 8) & 0xff;
-      const uint32_t a = footprint_mask_g<LPE>(occ, ch, cw, H, W, sl, gmask);
-      const uint32_t b = footprint_mask_g<LPE>(occ, cw, ch, H, W, sl, gmask);
-      if (have) { m0 = a; m1 = b; }
+      const uint32_t a = footprint_mask_g<LPE>(occ, ch, cw, H, W, sl, small, pmax);
+      const uint32_t b = footprint_mask_g<LPE>(occ, cw, ch, H, W, sl, small, pmax);
+      m0 = have ? a : 0u;
+      m1 = have ? b : 0u;
     }
-    return __any_sync(gmask, (m0 | m1) != 0u);
+    return group_any<LPE>((m0 | m1) != 0u, gmask);
   };
-  uint32_t m0, m1;
-  masks(m0, m1);
+  bool any = masks();
 
+  uint32_t slice = (uint32_t)p.slice0;
   for (int t = 0; t < p.n_steps; ++t) {
     const uint64_t step_no = p.step_no + (uint64_t)t;
-    const size_t he = (size_t)(step_no & 1) * N + (size_t)env;
+    const uint32_t he = ((uint32_t)step_no & 1u) * N + (uint32_t)env;
 
-    // ---- random policy ----
+    // ---- random policy; its pick is valid exactly when the mask has a set bit, and with
+    // an empty mask it reports (0,0,0), whose mask bit is 0: validate_action == `any` ----
     int o, x, y;
-    sample_action_g<LPE, S>(sh, m0, m1, p.seed, env, step_no, lane, gmask, o, x, y);
-    if (p.actions_log && sl == 0) {
+    sample_action_g<LPE, S>(sh, m0, m1, any, p.seed, env, step_no, lane, o, x, y);
+    if (p.actions_log && sl == 0 && live) {
       int32_t* a = p.actions_log + ((size_t)t * N + (size_t)env) * aw;
       if (kind == 0) { a[0] = x; a[1] = y; }
       else { a[0] = o; a[1] = x; a[2] = y; }
     }
-
-    // ---- validate_action == mask bit, recomputed (square:155-173, rect:434-457) ----
-    int ph = d.sq_n, pw = d.sq_n;
-    bool in_range = (unsigned)o < (unsigned)O && (unsigned)x < (unsigned)H && (unsigned)y < (unsigned)W;
-    if (kind != 0) {
-      in_range = in_range && cur < n_comp;
-      const uint32_t r = comps[in_range ? cur : 0];
-      const int ch = r & 0xff, cw = (r >> 8) & 0xff;
-      ph = (o & 1) ? cw : ch;
-      pw = (o & 1) ? ch : cw;
-    }
-    bool valid = in_range && x + ph <= H && y + pw <= W;
-    const uint32_t cols = valid ? (low_mask<uint32_t>(pw) << y) : 0u;
-    const bool mine = sl >= x && sl < x + ph;
-    const bool clash = __any_sync(gmask, mine && (occ & cols));
-    valid = valid && !clash;
-    if (valid) {
-      if (mine) occ |= cols;  // update_grid
+    const bool valid = any;
+    if (valid) {  // update_grid (square:175-185, rect:459-484); no sync inside
+      int ph = d.sq_n, pw = d.sq_n;
       if (kind != 0) {
-        if (sl == 0) comps[cur] = (comps[cur] & 0xffffu) | ((uint32_t)x << 16) | ((uint32_t)y << 24);
-        cur += 1;
+        const uint32_t r = comps[cur];
+        const int ch = r & 0xff, cw = (r >> 8) & 0xff;
+        ph = (o & 1) ? cw : ch;
+        pw = (o & 1) ? ch : cw;
       }
+      if (sl >= x && sl < x + ph) occ |= low_mask<uint32_t>(pw) << y;
+    }
+    __syncwarp();  // every lane has read comps[cur]
+    if (valid && kind != 0) {
+      if (sl == 0) comps[cur] = (comps[cur] & 0xffffu) | ((uint32_t)x << 16) | ((uint32_t)y << 24);
+      cur += 1;
     }
     ep_len += 1;
     const double reward = valid ? 1.0 : 0.0;  // square:115-153, rect:405-432
     ep_ret += reward;
-    __syncwarp(gmask);
 
-    // ---- done / auto-reset ----
+    // ---- done / auto-reset (no shuffle or vote inside report / restart) ----
     auto report = [&]() {  // end of an episode: info + statistics (first report only)
-      if (sl == 0) {
+      if (sl == 0 && live) {
         p.base.ep_return[he] = ep_ret;
         p.base.ep_length[he] = (int32_t)ep_len;
         if (!(flags & kFlagFinished)) {
@@ -285,7 +305,7 @@ rollout_small_kernel(const __grid_constant__ RolloutParams p) {
       if (!d.autoreset) flags |= kFlagFinished;
     };
     auto restart = [&]() {  // reset(): next bank slot, empty board (rect:310-351)
-      slot += (uint32_t)p.n_envs;
+      slot += N;
       if (p.bank_count) slot %= p.bank_count;
       epno += 1;
       if (kind != 0) {
@@ -298,10 +318,9 @@ rollout_small_kernel(const __grid_constant__ RolloutParams p) {
           for (int c = sl + kPre * LPE; c < C; c += LPE)
             comps[c] = reinterpret_cast<const uint32_t*>(rec + sh.rec_comps())[c];
         }
+        prefetch(slot);
       }
       cur = 0; flags = 0; ep_len = 0; ep_ret = 0.0; occ = 0u;
-      __syncwarp(gmask);
-      prefetch(slot);
     };
     const bool all_placed = kind != 0 && cur == n_comp;
     const bool early = !valid || all_placed;  // done without looking at the next mask
@@ -309,26 +328,34 @@ rollout_small_kernel(const __grid_constant__ RolloutParams p) {
       report();
       if (d.autoreset) restart();
     }
-    bool any = masks(m0, m1);
+    __syncwarp();
+    any = masks();
     const bool blocked = !early && !any;  // compute_if_done: nothing fits (rect:586-599)
-    if (blocked) {
-      report();
-      if (d.autoreset) { restart(); masks(m0, m1); }
+    if (__any_sync(kFull, blocked)) {     // warp-uniform; the other groups recompute the same masks
+      if (blocked) {
+        report();
+        if (d.autoreset) restart();
+      }
+      __syncwarp();
+      any = masks();
     }
     const bool done = early || blocked;
-    if (sl == 0) {
+    if (sl == 0 && live) {
       p.base.done[he] = done ? 1 : 0;
       p.base.reward[he] = reward;
     }
 
     // ---- observation of slice (slice0 + 1 + t) % ring ----
-    const size_t se = (size_t)((p.slice0 + 1 + t) % p.ring) * N + (size_t)env;
-    write_board_g<LPE, S>(sh, p.base.grid + se * HW, occ, flat, sl, gmask, lut);
-    uint8_t* mk = p.base.mask + se * (size_t)(O * HW);
-    write_board_g<LPE, S>(sh, mk, m0, flat, sl, gmask, lut);
-    if (O >= 2) write_board_g<LPE, S>(sh, mk + HW, m1, flat, sl, gmask, lut);
-    if (kind != 0) {
-      float* feat = p.base.feat + se * (size_t)(C * 5);
+    slice = slice + 1u == (uint32_t)p.ring ? 0u : slice + 1u;
+    const uint32_t se = slice * N + (uint32_t)env;
+    write_board_g<LPE, S>(sh, p.base.grid + (size_t)se * HW, occ, flat, sl, live, lut);
+    uint8_t* mk = p.base.mask + (size_t)se * (uint32_t)(O * HW);
+    write_board_g<LPE, S>(sh, mk, m0, flat, sl, live, lut);
+    if (O >= 2) write_board_g<LPE, S>(sh, mk + HW, m1, flat, sl, live, lut);
+    if (kind != 0 && live) {
+      float* feat = p.base.feat + (size_t)se * (uint32_t)(C * 5);
+      uint8_t* pm = p.base.place_mask + (size_t)se * (uint32_t)C;
+      uint8_t* cm = p.base.comp_mask + (size_t)se * (uint32_t)C;
       for (int c = sl; c < C; c += LPE) {
         float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f, f4 = 0.f;
         if (c < n_comp) {  // [h, w, x|-1, y|-1, h*w/(H*W)] (rect:53-71)
@@ -342,15 +369,15 @@ rollout_small_kernel(const __grid_constant__ RolloutParams p) {
         }
         float* row = feat + c * 5;
         __stcs(row + 0, f0); __stcs(row + 1, f1); __stcs(row + 2, f2); __stcs(row + 3, f3); __stcs(row + 4, f4);
-        st_stream(p.base.place_mask + se * C + c, (uint8_t)(c < cur ? 1 : 0));     // rect:284
-        st_stream(p.base.comp_mask + se * C + c, (uint8_t)(c < n_comp ? 1 : 0));   // rect:296-298
+        st_stream(pm + c, (uint8_t)(c < cur ? 1 : 0));     // rect:284
+        st_stream(cm + c, (uint8_t)(c < n_comp ? 1 : 0));  // rect:296-298
       }
     }
-    __syncwarp(gmask);  // the next step's placement rewrites comps[cur]
+    __syncwarp();  // the next step's placement rewrites comps[cur]
   }
 
   // ---- state: registers / shared memory -> HBM (once) ----
-  __syncwarp(gmask);
+  if (!live) return;
   if (sl == 0) {
     uint4 h4, d4;
     h4.x = hdr0; h4.y = (uint32_t)cur | ((uint32_t)flags << 8); h4.z = slot; h4.w = ep_len;
