@@ -184,8 +184,15 @@ def gpu_arm(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     N = args.envs
     cfg = CONFIGS[name]
-    # the observation ring must not fit in L2 (126 MB): small workloads get more slices
-    ring = max(OBS_RING, -(-300_000_000 // (N * ALGO_BYTES[name])))
+    # The observation ring must not fit in L2 (126 MB): small workloads get more slices.
+    # The pin-less kinds run the whole rollout in one launch whose CTAs are not in lock-step:
+    # a short ring would be overwritten inside L2 (measured: 12 % of the stores reached DRAM
+    # with 5 slices), so there the ring keeps every observation of the timed rollout -- what a
+    # rollout collector needs anyway -- as long as that stays below 48 GB.
+    slice_bytes = N * ALGO_BYTES[name]
+    ring = max(OBS_RING, -(-300_000_000 // slice_bytes))
+    if cfg["type"] in ("square", "rectangle") and not args.no_fused:
+        ring = max(ring, min(args.steps + 1, 48_000_000_000 // slice_bytes))
     env = pcbgpu.PcbVecEnv(cfg, N, device=local_rank, autoreset=True, obs_ring=ring,
                            bank_size=N * 4, seed=1000 + rank, generate_on_device=True)
     if args.no_fused:

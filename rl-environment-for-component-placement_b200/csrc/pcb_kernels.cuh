@@ -499,16 +499,17 @@ __device__ __forceinline__ uint32_t action_rand(uint64_t seed, uint32_t env, uin
 #ifndef PCB_SAMPLE_TRIES
 #define PCB_SAMPLE_TRIES 6
 #endif
-// Uniform draw over the valid (orientation, row, column) triples.  Fast path: rejection
-// sampling -- a uniform cell of the O x H x W box is accepted when its mask bit is set
-// (exactly uniform over the valid cells; the masks are dense early in an episode, so one
-// or two tries suffice).  After PCB_SAMPLE_TRIES misses the exact method runs: k-th set
-// bit in np.argwhere order via a warp prefix sum.
+// Uniform draw over the valid (orientation, row, column) triples.  Fast path (pin kinds):
+// rejection sampling -- a uniform cell of the O x H x W box is accepted when its mask bit is
+// set (exactly uniform over the valid cells; on the large, sparsely filled boards one or two
+// tries suffice).  After PCB_SAMPLE_TRIES misses, and always on the small pin-less boards
+// (where the multi-env-per-warp rollout kernel wants a loop-free sampler, pcb_small.cuh),
+// the exact method runs: k-th set bit in np.argwhere order via a warp prefix sum.
 template <int RPL, typename T, typename S>
 __device__ __forceinline__ void sample_action(const S& sh, const T (&m0)[RPL], const T (&m1)[RPL],
                                               uint64_t seed, int env, uint64_t step_no, int lane,
                                               int32_t* out) {
-  {
+  if (sh.kind() >= 2) {
     T anyv = T(0);
 #pragma unroll
     for (int k = 0; k < RPL; ++k) anyv |= m0[k] | m1[k];

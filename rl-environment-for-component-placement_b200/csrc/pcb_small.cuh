@@ -91,51 +91,39 @@ __device__ __forceinline__ uint32_t footprint_mask_g(uint32_t occ, int ph, int p
   return acc;
 }
 
-// sample_action (pcb_kernels.cuh) for every group of the warp at once: same counters, same
-// draw.  have = the group has at least one valid action.
+// sample_action (pcb_kernels.cuh) for every group of the warp at once: same counter, same
+// draw.  The pin-less kinds use the exact method only (k-th set bit in np.argwhere order,
+// k uniform in [0, total)): no data-dependent loop, so the groups stay converged.  The row
+// counts of both orientations travel through one prefix sum as two 16-bit fields.
 template <int LPE, typename S>
-__device__ __forceinline__ void sample_action_g(const S& sh, uint32_t m0, uint32_t m1, bool have,
-                                                uint64_t seed, int env, uint64_t step_no, int lane,
+__device__ __forceinline__ void sample_action_g(const S& sh, uint32_t m0, uint32_t m1, uint64_t seed,
+                                                int env, uint64_t step_no, int lane,
                                                 int& ao, int& ax, int& ay) {
-  ao = 0; ax = 0; ay = 0;
-  const int H = sh.H(), W = sh.W();
-  bool open = have;  // still looking for an accepted cell
-  for (int t = 0; t < PCB_SAMPLE_TRIES; ++t) {
-    if (!__any_sync(kFull, open)) break;
-    const uint64_t r = action_rand64(seed + 0x632BE59BD9B4E019ull * (uint64_t)(t + 1), (uint32_t)env, step_no);
-    const int o = (int)((((uint32_t)r & 0x1fffffu) * (uint32_t)sh.O()) >> 21);
-    const int row = (int)((((uint32_t)(r >> 21) & 0x1fffffu) * (uint32_t)H) >> 21);
-    const int col = (int)((((uint32_t)(r >> 42) & 0x1fffffu) * (uint32_t)W) >> 21);
-    const uint32_t bits = __shfl_sync(kFull, (o & 1) ? m1 : m0, row, LPE);
-    if (open && ((bits >> col) & 1u)) { ao = o; ax = row; ay = col; open = false; }
-  }
-  if (!__any_sync(kFull, open)) return;
-  // exact method for the groups that are still open: k-th set bit in np.argwhere order
   const int sl = lane & (LPE - 1);
-  int tot0 = __popc(m0), tot1 = __popc(m1);
+  const uint32_t c01 = (uint32_t)__popc(m0) | ((uint32_t)__popc(m1) << 16);
+  uint32_t incl = c01;
 #pragma unroll
   for (int off = 1; off < LPE; off <<= 1) {
-    tot0 += __shfl_xor_sync(kFull, tot0, off, LPE);
-    tot1 += __shfl_xor_sync(kFull, tot1, off, LPE);
+    const uint32_t v = __shfl_up_sync(kFull, incl, off, LPE);
+    if (sl >= off) incl += v;
   }
+  const uint32_t tot = __shfl_sync(kFull, incl, LPE - 1, LPE);
+  const int tot0 = (int)(tot & 0xffffu), tot1 = (int)(tot >> 16);
   const int total = sh.O() == 2 ? tot0 + tot1 : tot0;
   const uint32_t r = action_rand(seed, (uint32_t)env, step_no);
   int kth = (int)__umulhi(r, (uint32_t)total);
   const bool second = kth >= tot0;
   if (second) kth -= tot0;
   const uint32_t bits = second ? m1 : m0;
-  const int c = __popc(bits);
-  int incl = c;
-#pragma unroll
-  for (int off = 1; off < LPE; off <<= 1) {
-    const int v = __shfl_up_sync(kFull, incl, off, LPE);
-    if (sl >= off) incl += v;
-  }
-  const int excl = incl - c;
-  const unsigned who = __ballot_sync(kFull, kth >= excl && kth < incl) >> (lane & ~(LPE - 1));
+  const int inc = (int)(second ? incl >> 16 : incl & 0xffffu);
+  const int excl = inc - __popc(bits);
+  const unsigned who = __ballot_sync(kFull, kth >= excl && kth < inc) >> (lane & ~(LPE - 1));
   const int src = (__ffs(who) - 1) & (LPE - 1);  // row that holds the kth bit
   const int col = __shfl_sync(kFull, nth_bit32(bits, kth - excl), src, LPE);
-  if (open && total > 0) { ao = second ? 1 : 0; ax = src; ay = col; }
+  const bool have = total > 0;  // an empty mask reports (0, 0, 0)
+  ao = have && second ? 1 : 0;
+  ax = have ? src : 0;
+  ay = have ? col : 0;
 }
 
 // one board (bit row per lane) -> H*W bytes of 0/1
@@ -255,16 +243,34 @@ rollout_small_kernel(const __grid_constant__ RolloutParams p) {
     return group_any<LPE>((m0 | m1) != 0u, gmask);
   };
   bool any = masks();
+  // square env: the mask after a reset is a constant
+  uint32_t m_empty = 0u;
+  bool any_empty = false;
+  if (kind == 0) {
+    m_empty = footprint_mask_g<LPE>(0u, d.sq_n, d.sq_n, H, W, sl, small, pmax);
+    any_empty = group_any<LPE>(m_empty != 0u, gmask);
+  }
+
+  float frow[kPre][5];
+  auto feature_row = [&](uint32_t r, float (&f)[5]) {
+    const int h = r & 0xff, w = (r >> 8) & 0xff, cx = (r >> 16) & 0xff, cy = r >> 24;
+    f[0] = (float)h; f[1] = (float)w;
+    f[2] = cx == 0xFF ? -1.f : (float)cx;
+    f[3] = cy == 0xFF ? -1.f : (float)cy;
+    if (S::fixed && (HW & (HW - 1)) == 0) f[4] = (float)(h * w) * (1.0f / (float)HW);
+    else f[4] = p.ratio_lut[h * w];
+  };
+  bool feat_dirty = true;  // group-uniform
 
   uint32_t slice = (uint32_t)p.slice0;
   for (int t = 0; t < p.n_steps; ++t) {
     const uint64_t step_no = p.step_no + (uint64_t)t;
-    const uint32_t he = ((uint32_t)step_no & 1u) * N + (uint32_t)env;
+    const uint32_t he = ((uint32_t)step_no & 1u) ? N + (uint32_t)env : (uint32_t)env;
 
     // ---- random policy; its pick is valid exactly when the mask has a set bit, and with
     // an empty mask it reports (0,0,0), whose mask bit is 0: validate_action == `any` ----
     int o, x, y;
-    sample_action_g<LPE, S>(sh, m0, m1, any, p.seed, env, step_no, lane, o, x, y);
+    sample_action_g<LPE, S>(sh, m0, m1, p.seed, env, step_no, lane, o, x, y);
     if (p.actions_log && sl == 0 && live) {
       int32_t* a = p.actions_log + ((size_t)t * N + (size_t)env) * aw;
       if (kind == 0) { a[0] = x; a[1] = y; }
@@ -284,6 +290,9 @@ rollout_small_kernel(const __grid_constant__ RolloutParams p) {
     __syncwarp();  // every lane has read comps[cur]
     if (valid && kind != 0) {
       if (sl == 0) comps[cur] = (comps[cur] & 0xffffu) | ((uint32_t)x << 16) | ((uint32_t)y << 24);
+#pragma unroll
+      for (int k = 0; k < kPre; ++k)
+        if (sl + k * LPE == cur) { frow[k][2] = (float)x; frow[k][3] = (float)y; }
       cur += 1;
     }
     ep_len += 1;
@@ -321,6 +330,7 @@ rollout_small_kernel(const __grid_constant__ RolloutParams p) {
         prefetch(slot);
       }
       cur = 0; flags = 0; ep_len = 0; ep_ret = 0.0; occ = 0u;
+      feat_dirty = true;
     };
     const bool all_placed = kind != 0 && cur == n_comp;
     const bool early = !valid || all_placed;  // done without looking at the next mask
@@ -337,7 +347,8 @@ rollout_small_kernel(const __grid_constant__ RolloutParams p) {
         if (d.autoreset) restart();
       }
       __syncwarp();
-      any = masks();
+      if (kind != 0) any = masks();
+      else if (blocked && d.autoreset) { m0 = m_empty; any = any_empty; }
     }
     const bool done = early || blocked;
     if (sl == 0 && live) {
@@ -352,27 +363,46 @@ rollout_small_kernel(const __grid_constant__ RolloutParams p) {
     uint8_t* mk = p.base.mask + (size_t)se * (uint32_t)(O * HW);
     write_board_g<LPE, S>(sh, mk, m0, flat, sl, live, lut);
     if (O >= 2) write_board_g<LPE, S>(sh, mk + HW, m1, flat, sl, live, lut);
-    if (kind != 0 && live) {
-      float* feat = p.base.feat + (size_t)se * (uint32_t)(C * 5);
-      uint8_t* pm = p.base.place_mask + (size_t)se * (uint32_t)C;
-      uint8_t* cm = p.base.comp_mask + (size_t)se * (uint32_t)C;
-      for (int c = sl; c < C; c += LPE) {
-        float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f, f4 = 0.f;
-        if (c < n_comp) {  // [h, w, x|-1, y|-1, h*w/(H*W)] (rect:53-71)
-          const uint32_t r = comps[c];
-          const int h = r & 0xff, w = (r >> 8) & 0xff, cx = (r >> 16) & 0xff, cy = r >> 24;
-          f0 = (float)h; f1 = (float)w;
-          f2 = cx == 0xFF ? -1.f : (float)cx;
-          f3 = cy == 0xFF ? -1.f : (float)cy;
-          if (S::fixed && (HW & (HW - 1)) == 0) f4 = (float)(h * w) * (1.0f / (float)HW);
-          else f4 = p.ratio_lut[h * w];
+    if (kind != 0) {
+      // all_components_feature rows [h, w, x|-1, y|-1, h*w/(H*W)] (rect:53-71) live in registers
+      // (lane sl owns components sl, sl + LPE) and are rebuilt only when they change: a reset
+      // rewrites every row, a placement the (x, y) of one
+      if (feat_dirty) {
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) {
+          const int c = sl + k * LPE;
+#pragma unroll
+          for (int j = 0; j < 5; ++j) frow[k][j] = 0.f;
+          if (c < n_comp) feature_row(comps[c], frow[k]);
         }
-        float* row = feat + c * 5;
-        __stcs(row + 0, f0); __stcs(row + 1, f1); __stcs(row + 2, f2); __stcs(row + 3, f3); __stcs(row + 4, f4);
-        st_stream(pm + c, (uint8_t)(c < cur ? 1 : 0));     // rect:284
-        st_stream(cm + c, (uint8_t)(c < n_comp ? 1 : 0));  // rect:296-298
+      }
+      if (live) {
+        float* feat = p.base.feat + (size_t)se * (uint32_t)(C * 5);
+        uint8_t* pm = p.base.place_mask + (size_t)se * (uint32_t)C;
+        uint8_t* cm = p.base.comp_mask + (size_t)se * (uint32_t)C;
+#pragma unroll
+        for (int k = 0; k < kPre; ++k) {
+          const int c = sl + k * LPE;
+          if (c < C) {
+            float* row = feat + c * 5;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) __stcs(row + j, frow[k][j]);
+            st_stream(pm + c, (uint8_t)(c < cur ? 1 : 0));     // rect:284
+            st_stream(cm + c, (uint8_t)(c < n_comp ? 1 : 0));  // rect:296-298
+          }
+        }
+        for (int c = sl + kPre * LPE; c < C; c += LPE) {  // more than kPre * LPE components
+          float f[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+          if (c < n_comp) feature_row(comps[c], f);
+          float* row = feat + c * 5;
+#pragma unroll
+          for (int j = 0; j < 5; ++j) __stcs(row + j, f[j]);
+          st_stream(pm + c, (uint8_t)(c < cur ? 1 : 0));
+          st_stream(cm + c, (uint8_t)(c < n_comp ? 1 : 0));
+        }
       }
     }
+    feat_dirty = false;
     __syncwarp();  // the next step's placement rewrites comps[cur]
   }
 
