@@ -654,19 +654,22 @@ __device__ __forceinline__ void write_obs(const S& sh, const Params& p, Env<T>& 
       row[0] = f0; row[1] = f1; row[2] = f2; row[3] = f3; row[4] = f4;
     }
   } else {
-    for (int i = lane; i < sh.feat_n(); i += 32) {
-      int c = i / F, f = i - F * c;
-      float v = 0.f;
-      if (c < n_comp) {
+    // spatial (spatial:203-239): the 5 values, then the component's pin ids (written by the
+    // pins in phase B) padded with -1; one lane per component row, F = 5 + P floats
+    for (int c = lane; c < C; c += 32) {
+      float* row = fdst + c * F;
+      const bool have = c < n_comp;
+      float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f, f4 = 0.f;
+      if (have) {
         CompRec r = e.comps[c];
-        if (f == 0) v = (float)r.h;
-        else if (f == 1) v = (float)r.w;
-        else if (f == 2) v = r.x == 0xFF ? -1.f : (float)r.x;
-        else if (f == 3) v = r.y == 0xFF ? -1.f : (float)r.y;
-        else if (f == 4) v = area_ratio(sh, p, r.h * r.w);
-        else v = -1.f;
+        f0 = (float)r.h; f1 = (float)r.w;
+        f2 = r.x == 0xFF ? -1.f : (float)r.x;
+        f3 = r.y == 0xFF ? -1.f : (float)r.y;
+        f4 = area_ratio(sh, p, r.h * r.w);
       }
-      fdst[i] = v;
+      row[0] = f0; row[1] = f1; row[2] = f2; row[3] = f3; row[4] = f4;
+      const float pad = have ? -1.f : 0.f;
+      for (int f = 5; f < F; ++f) row[f] = pad;
     }
   }
 
@@ -715,32 +718,39 @@ __device__ __forceinline__ void write_obs(const S& sh, const Params& p, Env<T>& 
   __syncwarp();
 
   // pin_grid (spatial:1663-1675): channel 0 = occupied cell without a pin,
-  // channel net+1 = placed pin of that net.
+  // channel net+1 = placed pin of that net.  Staged and written in two halves of the rows,
+  // which halves the largest shared-memory buffer of the kernel (CTAs per SM: 7 -> 12 on D).
   const int K = sh.K(), W = sh.W();
-  zero_smem(e.stage, (sh.pgrid_b() + 15) & ~15, lane);
-  __syncwarp();
+  const int part_rows = (sh.H() + 1) >> 1;
+  for (int part = 0; part < 2; ++part) {
+    const int r0 = part * part_rows, r1 = min(sh.H(), r0 + part_rows);
+    const int nbytes = (r1 - r0) * W * K;
+    zero_smem(e.stage, (nbytes + 15) & ~15, lane);
+    __syncwarp();
 #pragma unroll
-  for (int k = 0; k < RPL; ++k) {
-    int row = lane + 32 * k;
-    T bits = row < sh.H() ? occ[k] : T(0);
-    while (bits) {
-      int j = ffs_t<T>(bits);
-      bits &= bits - 1;
-      e.stage[(row * W + j) * K] = 1;
+    for (int k = 0; k < RPL; ++k) {
+      const int row = lane + 32 * k;
+      T bits = (row >= r0 && row < r1) ? occ[k] : T(0);
+      while (bits) {
+        int j = ffs_t<T>(bits);
+        bits &= bits - 1;
+        e.stage[((row - r0) * W + j) * K] = 1;
+      }
     }
+    __syncwarp();
+    for (int q = lane; q < n_pins; q += 32) {
+      PinRec pr = e.pins[q];
+      CompRec r = e.comps[pr.comp];
+      const int ax = r.x + pr.rx;
+      if (r.x == 0xFF || ax < r0 || ax >= r1) continue;
+      uint8_t* cell = e.stage + ((ax - r0) * W + (r.y + pr.ry)) * K;
+      cell[0] = 0;
+      cell[pr.net + 1] = 1;
+    }
+    __syncwarp();
+    copy_out(p.out.pgrid + (size_t)env * sh.pgrid_b() + (size_t)r0 * W * K, e.stage, nbytes, lane);
+    __syncwarp();
   }
-  __syncwarp();
-  for (int q = lane; q < n_pins; q += 32) {
-    PinRec pr = e.pins[q];
-    CompRec r = e.comps[pr.comp];
-    if (r.x == 0xFF) continue;
-    uint8_t* cell = e.stage + ((r.x + pr.rx) * W + (r.y + pr.ry)) * K;
-    cell[0] = 0;
-    cell[pr.net + 1] = 1;
-  }
-  __syncwarp();
-  copy_out(p.out.pgrid + (size_t)env * sh.pgrid_b(), e.stage, sh.pgrid_b(), lane);
-  __syncwarp();
 
   // component_grid (spatial:1677-1697): drawn at reset from the UN-rotated pin
   // coordinates, i.e. from the bank record, and constant during the episode.

@@ -120,7 +120,8 @@ PCB_HD constexpr Layout make_layout(int kind, int H, int W, int C, int mh, int m
   L.cgrid_b = kind == 3 ? C * mh * mw * K : 0;
   // staging: pin feature rows + component features side by side; the spatial boards reuse it
   int stage = align16c((L.pnum_n + L.pcat_n) * 2) + align16c(L.feat_n * 4) + 16;
-  if (kind == 3) stage = maxc(stage, maxc(L.pgrid_b, L.cgrid_b));
+  // pin_grid is staged in two halves of the rows
+  if (kind == 3) stage = maxc(stage, maxc(align16c(((H + 1) / 2) * W * K), L.cgrid_b));
   L.sm_mrow = L.st_stride;
   // generic boards: mask rows, then a dense bit string of one board (H*W bits + slack)
   L.sm_scr = L.sm_mrow + (fast_board ? 0 : 2 * rows * word);

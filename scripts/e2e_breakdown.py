@@ -1,0 +1,79 @@
+"""Where the end-to-end step time goes (config C, 65 536 envs): device step with a sync per
+step, + H2D of the actions, + D2H of reward/done, and the full pcb_step_host."""
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import __graft_entry__ as ge  # noqa: E402
+
+ge.build()
+import pcbgpu  # noqa: E402
+from ref_harness import CONFIGS  # noqa: E402
+
+N, K = 65536, 200
+env = pcbgpu.PcbVecEnv(CONFIGS["C"], N, autoreset=True, obs_ring=4, bank_size=4 * N, seed=1,
+                       generate_on_device=True)
+env.reset()
+log = torch.zeros((K, N, 3), dtype=torch.int32, device="cuda")
+env.rollout_random(K, seed=3, actions_log=log)
+flat = ((log[..., 0] * 32 + log[..., 1]) * 32 + log[..., 2]).int().contiguous()
+h_act = torch.empty((K, N), dtype=torch.int32, pin_memory=True)
+h_act.copy_(flat)
+h_r = torch.empty((N,), dtype=torch.float64, pin_memory=True)
+h_d = torch.empty((N,), dtype=torch.uint8, pin_memory=True)
+d_act = torch.empty((N,), dtype=torch.int32, device="cuda")
+
+
+def run(label, body):
+    env.reset()
+    env.rollout_random(16, seed=3)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for t in range(K):
+        body(t)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / K * 1e6
+    print(f"{label:52s} {dt:8.1f} us/step  {N / dt * 1e6:.3e} env-steps/s", flush=True)
+
+
+def dev_only(t):
+    env.step_async(flat[t])
+    torch.cuda.synchronize()
+
+
+def with_h2d(t):
+    d_act.copy_(h_act[t], non_blocking=True)
+    env.step_async(d_act)
+    torch.cuda.synchronize()
+
+
+def with_both(t):
+    d_act.copy_(h_act[t], non_blocking=True)
+    env.step_async(d_act)
+    r = env.results()
+    h_r.copy_(r["reward"], non_blocking=True)
+    h_d.copy_(r["done"], non_blocking=True)
+    torch.cuda.synchronize()
+
+
+a_np, r_np, d_np = h_act.numpy(), h_r.numpy(), h_d.numpy()
+
+
+def step_host(t):
+    env.step_host(a_np[t], r_np, d_np)
+
+
+def no_sync(t):
+    env.step_async(flat[t])
+
+
+run("pcb_step, device actions, no sync", no_sync)
+run("pcb_step, device actions, sync every step", dev_only)
+run("+ H2D of the actions (torch copy)", with_h2d)
+run("+ D2H of reward and done (torch copies)", with_both)
+run("pcb_step_host", step_host)
