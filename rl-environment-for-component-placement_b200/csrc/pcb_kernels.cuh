@@ -152,13 +152,18 @@ __device__ __forceinline__ void st_stream(uint32_t* p, uint32_t v) {
 }
 
 // smem -> global copy of one environment's slice of a tensor, widest store the
-// alignment allows (16 B when the per-env size is a multiple of 16).
+// alignment allows (16 B when the per-env size is a multiple of 16, else 8 or 4; the staging
+// buffers are 16-byte aligned).
 __device__ __forceinline__ void copy_out(void* dst, const void* src, int nbytes, int lane) {
   uintptr_t a = reinterpret_cast<uintptr_t>(dst) | (uintptr_t)nbytes;
   if ((a & 15) == 0) {
     const uint4* s = reinterpret_cast<const uint4*>(src);
     uint4* d = reinterpret_cast<uint4*>(dst);
     for (int i = lane; i < (nbytes >> 4); i += 32) st_stream(d + i, s[i]);
+  } else if ((a & 7) == 0) {
+    const uint2* s = reinterpret_cast<const uint2*>(src);
+    uint2* d = reinterpret_cast<uint2*>(dst);
+    for (int i = lane; i < (nbytes >> 3); i += 32) st_stream(d + i, s[i]);
   } else if ((a & 3) == 0) {
     const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
     uint32_t* d = reinterpret_cast<uint32_t*>(dst);
