@@ -30,6 +30,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 WORKLOAD = "C"
 ENVS_PER_GPU = 65536
 OBS_RING = 4
+REPETITIONS = 5
 # SURVEY.md section 8d / BASELINE.md section 5: algorithmic bytes per env-step (compact contract)
 ALGO_BYTES = {"A": 161, "B": 1049, "C": 7699, "D": 15775, "E": 28821,
               # the reference's shipped 10x10 pin config (agent/config/rectangle_pin_model.json):
@@ -230,9 +231,18 @@ def gpu_arm(args, rank, world, local_rank):
     barrier()
     wall = time.perf_counter() - t_wall0
     launches = env.launch_count - l0
-    ms = e0.elapsed_time(e1)
-    clk = clocks.stop() if rank == 0 else None
+    reps_ms = [e0.elapsed_time(e1)]
     stats = env.episode_stats(reset=True)
+    # median of 5 repetitions of the same K-step region (the rollout just goes on)
+    for _ in range(REPETITIONS - 1):
+        barrier()
+        e0.record(stream)
+        env.rollout_random(K, seed)
+        e1.record(stream)
+        barrier()
+        reps_ms.append(e0.elapsed_time(e1))
+    clk = clocks.stop() if rank == 0 else None
+    env.episode_stats(reset=True)
 
     # ---- pass 2: same rollout with per-kernel CUDA events (roofline) + action log ----
     prepare()
@@ -289,11 +299,12 @@ def gpu_arm(args, rank, world, local_rank):
     stats3 = env.episode_stats(reset=True)
 
     # ---- reduce over ranks ------------------------------------------------------
-    vals = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=env.device)
+    vals = torch.tensor(reps_ms + [e2e_s * 1e3], dtype=torch.float64, device=env.device)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         agg = pcbgpu.allreduce_episode_stats  # noqa: F841 (C1: the only collective, off the step path)
-    ms_max, e2e_ms_max = vals.tolist()
+    *reps_max, e2e_ms_max = vals.tolist()
+    ms_max = sorted(reps_max)[len(reps_max) // 2]  # median repetition, each the max over ranks
     total_steps = float(N) * K * world
     value = total_steps / (ms_max * 1e-3)
     e2e_value = total_steps / (e2e_ms_max * 1e-3)
@@ -330,8 +341,10 @@ def gpu_arm(args, rank, world, local_rank):
             "episode_phases": "staggered (1/%d of the envs finish every step)" % EP_LEN[name],
             "l2": "working set larger than L2: every step writes a fresh %.1f MB observation slice "
                   "(ring of %d slices)" % (N * (ALGO_BYTES[name]) / 1e6, ring),
-            "timing": "CUDA events on the launching stream around %d steps, max over ranks" % K,
+            "timing": "CUDA events on the launching stream around %d steps, max over ranks; "
+                      "median of %d back-to-back repetitions" % (K, REPETITIONS),
         },
+        "repetitions_ms": reps_max,
         "e2e": {"value": e2e_value, "unit": "env-steps/s",
                 "h2d_bytes_per_step": int(N * 4), "d2h_bytes_per_step": int(N * 9),
                 "path": "pcb_step_host (C ABI): pinned host flat actions (int32 per env) -> H2D -> step -> D2H reward+done, "
@@ -356,11 +369,52 @@ def gpu_arm(args, rank, world, local_rank):
                      "mean_length": stats["sum_length"] / max(stats["episodes"], 1)},
         "wall_s_timed_region": wall,
     }
+    if world == 1 and name == WORKLOAD and not args.no_secondary:
+        env.close()
+        del env
+        torch.cuda.empty_cache()
+        out["other_workloads"] = [secondary(args, "B", 4096), secondary(args, "D", ENVS_PER_GPU)]
     if world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(name, args.cpu_seconds)
     else:
         out["cpu_baseline"] = None
     print(json.dumps(out), flush=True)
+
+
+def secondary(args, name, N):
+    """Device-timed value of another BASELINE.json configuration (B = configs[1] at its 4 096
+    envs, D = configs[3]); same method as the main line, one repetition, no e2e / roofline."""
+    import torch
+
+    import pcbgpu
+    from ref_harness import CONFIGS
+
+    K, W = args.steps, args.warmup
+    slice_bytes = N * ALGO_BYTES[name]
+    ring = max(OBS_RING, -(-300_000_000 // slice_bytes))
+    if CONFIGS[name]["type"] in ("square", "rectangle"):
+        ring = max(ring, min(K + 1, 48_000_000_000 // slice_bytes))
+    env = pcbgpu.PcbVecEnv(CONFIGS[name], N, device=torch.cuda.current_device(), autoreset=True,
+                           obs_ring=ring, bank_size=N * 4, seed=1000, generate_on_device=True)
+    env.reset()
+    stagger(env, name, 7)
+    env.rollout_random(W, 7)
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = env.launch_count
+    e0.record(stream)
+    env.rollout_random(K, 7)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    peak, _ = load_peaks()
+    value = float(N) * K / (ms * 1e-3)
+    res = {"workload": WORKLOAD_DESC[name], "envs_per_gpu": N, "value": value, "unit": "env-steps/s",
+           "ms_per_step": ms / K, "gpu_launches": env.launch_count - l0, "obs_ring": ring,
+           "whole_step_frac": value * ALGO_BYTES[name] / 1e9 / peak}
+    env.close()
+    return res
 
 
 def _cpu_slices(args):
@@ -441,6 +495,8 @@ def main():
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the short device-timed lines of configs B (4 096 envs) and D")
     ap.add_argument("--no-fused", action="store_true",
                     help="pin-less kinds: per-step launches instead of the multi-step rollout kernel")
     args = ap.parse_args()
