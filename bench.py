@@ -200,6 +200,10 @@ def gpu_arm(args, rank, world, local_rank):
         env.fused_rollout(False)
     seed = 7 + rank
     K, W = args.steps, args.warmup
+    # An explicit stream: on the legacy default stream the overlapped reward kernels of the
+    # beam reward types run in one of two regimes per call (194 or ~300 us per step, measured:
+    # profiles/README.md), on a created stream they do not.
+    torch.cuda.set_stream(torch.cuda.Stream())
     stream = torch.cuda.current_stream()
 
     def barrier():

@@ -27,19 +27,35 @@ __device__ __forceinline__ uint64_t py_tuple_hash(int x, int y) {
   return acc == ~0ull ? 1546275796ull : acc;
 }
 
+// The table lives in registers: `occ` has one bit per slot, the key of slot i (a point index,
+// < 16) is nibble i of (k0, k1).  Emptiness tests, the linear probe and the in-order walks
+// over the live slots are bit operations on `occ`; nothing is indexed dynamically in memory.
 struct PyTab {
-  int8_t s[kTab];  // key index or -1 (empty)
+  uint32_t occ;
+  uint64_t k0, k1;
   int mask, used;
+  __device__ __forceinline__ int key(int i) const {
+    return (int)(((i < 16 ? k0 : k1) >> ((i & 15) * 4)) & 15ull);
+  }
+  __device__ __forceinline__ void put(int i, int k) {
+    const int sh = (i & 15) * 4;
+    if (i < 16) k0 = (k0 & ~(15ull << sh)) | ((uint64_t)k << sh);
+    else k1 = (k1 & ~(15ull << sh)) | ((uint64_t)k << sh);
+    occ |= 1u << i;
+  }
 };
+static_assert(kMaxBeamPoints < 16 && kTab == 32, "PyTab packs 32 slots of 4-bit keys");
 
-__device__ __forceinline__ int tab_free_slot(const int8_t* s, int mask, uint64_t h) {
+// set_add_entry's probe for a free slot: the home slot, the 9 slots after it (LINEAR_PROBES)
+// when they are inside the table, then the perturbed recurrence
+__device__ __forceinline__ int tab_free_slot(uint32_t occ, int mask, uint64_t h) {
   uint64_t perturb = h;
   int i = (int)(h & (uint64_t)mask);
   while (true) {
-    if (s[i] < 0) return i;
+    if (!((occ >> i) & 1u)) return i;
     if (i + 9 <= mask) {
-      for (int j = 1; j <= 9; ++j)
-        if (s[i + j] < 0) return i + j;
+      const uint32_t free9 = (~occ >> (i + 1)) & 0x1ffu;  // slots i+1 .. i+9
+      if (free9) return i + __ffs((int)free9);
     }
     perturb >>= 5;
     i = (int)(((uint64_t)i * 5 + 1 + perturb) & (uint64_t)mask);
@@ -47,7 +63,7 @@ __device__ __forceinline__ int tab_free_slot(const int8_t* s, int mask, uint64_t
 }
 
 __device__ __forceinline__ void tab_clear(PyTab& t, int size) {
-  for (int i = 0; i < kTab; ++i) t.s[i] = -1;
+  t.occ = 0u; t.k0 = 0ull; t.k1 = 0ull;
   t.mask = size - 1;
   t.used = 0;
 }
@@ -57,17 +73,17 @@ __device__ __forceinline__ void tab_clear(PyTab& t, int size) {
 __device__ __forceinline__ void tab_resize(PyTab& t, int minused, const uint64_t* h) {
   int size = 8;
   while (size <= minused) size <<= 1;
-  int8_t old[kTab];
-  int n = 0;
-  for (int i = 0; i <= t.mask; ++i)
-    if (t.s[i] >= 0) old[n++] = t.s[i];
+  const PyTab old = t;
   tab_clear(t, size);
-  for (int i = 0; i < n; ++i) t.s[tab_free_slot(t.s, t.mask, h[old[i]])] = old[i];
-  t.used = n;
+  for (uint32_t live = old.occ; live; live &= live - 1) {
+    const int k = old.key(__ffs((int)live) - 1);
+    t.put(tab_free_slot(t.occ, t.mask, h[k]), k);
+  }
+  t.used = old.used;
 }
 
 __device__ __forceinline__ void tab_add(PyTab& t, int key, const uint64_t* h) {  // set_add_entry
-  t.s[tab_free_slot(t.s, t.mask, h[key])] = (int8_t)key;
+  t.put(tab_free_slot(t.occ, t.mask, h[key]), key);
   t.used += 1;
   if (t.used * 5 >= t.mask * 3) tab_resize(t, t.used * 4, h);
 }
@@ -86,38 +102,44 @@ __device__ __forceinline__ int tab_difference(const PyTab& targets, uint32_t see
       tab_clear(r, size);
     }
     if (r.mask == targets.mask) {
-      for (int i = 0; i <= targets.mask; ++i)
-        if (targets.s[i] >= 0 && !((seen >> targets.s[i]) & 1u)) out[n++] = targets.s[i];
+      for (uint32_t live = targets.occ; live; live &= live - 1) {
+        const int k = targets.key(__ffs((int)live) - 1);
+        if (!((seen >> k) & 1u)) out[n++] = (int8_t)k;
+      }
       return n;
     }
-    for (int i = 0; i <= targets.mask; ++i)
-      if (targets.s[i] >= 0) r.s[tab_free_slot(r.s, r.mask, h[targets.s[i]])] = targets.s[i];
-    for (int i = 0; i <= r.mask; ++i)
-      if (r.s[i] >= 0 && !((seen >> r.s[i]) & 1u)) out[n++] = r.s[i];
+    for (uint32_t live = targets.occ; live; live &= live - 1) {
+      const int k = targets.key(__ffs((int)live) - 1);
+      r.put(tab_free_slot(r.occ, r.mask, h[k]), k);
+    }
+    for (uint32_t live = r.occ; live; live &= live - 1) {
+      const int k = r.key(__ffs((int)live) - 1);
+      if (!((seen >> k) & 1u)) out[n++] = (int8_t)k;
+    }
     return n;
   }
   tab_clear(r, 8);
-  for (int i = 0; i <= targets.mask; ++i) {
-    int k = targets.s[i];
-    if (k >= 0 && !((seen >> k) & 1u)) tab_add(r, k, h);
+  for (uint32_t live = targets.occ; live; live &= live - 1) {
+    const int k = targets.key(__ffs((int)live) - 1);
+    if (!((seen >> k) & 1u)) tab_add(r, k, h);
   }
-  for (int i = 0; i <= r.mask; ++i)
-    if (r.s[i] >= 0) out[n++] = r.s[i];
+  for (uint32_t live = r.occ; live; live &= live - 1) out[n++] = (int8_t)r.key(__ffs((int)live) - 1);
   return n;
 }
 
 struct BeamItem {
   double prio;
+  uint64_t path;  // nibble j = local index of the j-th point visited after the start point
   uint32_t seen;
-  int8_t path[kMaxBeamPoints + 1];  // local point indices after the start point
 };
+__device__ __forceinline__ int path_at(uint64_t path, int j) { return (int)((path >> (4 * j)) & 15ull); }
 
 // lexicographic (priority, path) order of heapq on (float, list-of-tuples) entries
 __device__ __forceinline__ bool beam_less(const BeamItem& a, const BeamItem& b, int len,
                                           const int16_t* x, const int16_t* y) {
   if (a.prio != b.prio) return a.prio < b.prio;
   for (int i = 0; i < len; ++i) {
-    int pa = a.path[i], pb = b.path[i];
+    int pa = path_at(a.path, i), pb = path_at(b.path, i);
     if (x[pa] != x[pb]) return x[pa] < x[pb];
     if (y[pa] != y[pb]) return y[pa] < y[pb];
   }
@@ -159,7 +181,7 @@ __device__ __forceinline__ void beam_route_net(const JobPin* pins, int lo, int m
 
   BeamItem q[kMaxBeamWidth * kMaxBeamWidth], nq[kMaxBeamWidth * kMaxBeamWidth];
   int qn = 1;
-  q[0].prio = 0.0; q[0].seen = 0u;
+  q[0].prio = 0.0; q[0].seen = 0u; q[0].path = 0ull;
   int best_idx = 0;
   for (int level = 0; level <= m; ++level) {  // level == number of visited points
     // order the queue (selection of the min(bw, qn) smallest entries)
@@ -179,7 +201,8 @@ __device__ __forceinline__ void beam_route_net(const JobPin* pins, int lo, int m
     int nn = 0;
     for (int t = 0; t < take; ++t) {
       const BeamItem& it = q[order[t]];
-      const int hx = level ? x[it.path[level - 1]] : sx, hy = level ? y[it.path[level - 1]] : sy;
+      const int last = level ? path_at(it.path, level - 1) : 0;
+      const int hx = level ? x[last] : sx, hy = level ? y[last] : sy;
       int8_t cand[kMaxBeamPoints + 1];
       double cd[kMaxBeamPoints + 1];
       int nc = tab_difference(targets, it.seen, h, cand);
@@ -197,8 +220,7 @@ __device__ __forceinline__ void beam_route_net(const JobPin* pins, int lo, int m
         BeamItem& c = nq[nn++];
         c.prio = it.prio + cd[i];
         c.seen = it.seen | (1u << cand[i]);
-        for (int j = 0; j < level; ++j) c.path[j] = it.path[j];
-        c.path[level] = cand[i];
+        c.path = it.path | ((uint64_t)cand[i] << (4 * level));
       }
     }
     for (int i = 0; i < nn; ++i) q[i] = nq[i];
@@ -207,7 +229,7 @@ __device__ __forceinline__ void beam_route_net(const JobPin* pins, int lo, int m
   *start_out = (uint16_t)(lo + start);
   uint16_t prev = (uint16_t)(lo + start);
   for (int j = 0; j < m; ++j) {
-    uint16_t g = gid[q[best_idx].path[j]];
+    uint16_t g = gid[path_at(q[best_idx].path, j)];
     nxt[prev] = g;
     prev = g;
   }
