@@ -38,6 +38,11 @@ class PcbVecEnv:
     instances  : list of instances (oracle ``Instance`` objects / dicts) or an
                  ``InstanceBank``; default: ``bank_size`` instances from the
                  library's generator seeded with ``seed``.
+    obs_dtype  : "compact" (default, the measured contract: u8 / i16 / f32 tensors that are
+                 views of the library's memory) or "reference": every observation is cast on
+                 the device to the reference's dtype (float64; float32 for the square env) and
+                 the area ratio is the exact float64 quotient -- equal to the reference's
+                 arrays value for value, at 8x the bytes.
     autoreset  : True  -> a finished env restarts on its next bank slot and the
                           returned observation is the first of the new episode;
                  False -> the terminal observation is returned as the reference
@@ -46,9 +51,12 @@ class PcbVecEnv:
 
     def __init__(self, env_config, num_envs, device=0, autoreset=True, obs_ring=1,
                  instances=None, bank_size=None, seed=0, norm_uses_fma=True, force_generic=False,
-                 generate_on_device=False, specialize=False):
+                 generate_on_device=False, specialize=False, obs_dtype="compact"):
         if not torch.cuda.is_available():
             raise RuntimeError("pcbgpu needs a CUDA device; there is no CPU fallback")
+        if obs_dtype not in ("compact", "reference"):
+            raise ValueError("obs_dtype must be 'compact' or 'reference'")
+        self.obs_dtype = obs_dtype
         self.spec = make_spec(env_config, autoreset, obs_ring, norm_uses_fma)
         # specialize=True: kernels compiled for exactly this configuration (nvcc, cached);
         # otherwise built-in shapes for the canonical configs, runtime-shaped kernels else
@@ -115,7 +123,45 @@ class PcbVecEnv:
     # -- gym surface ---------------------------------------------------------
     def _obs(self):
         s = self.lib.pcb_current_slice(self._h)
-        return {k: v[s] for k, v in self._ring.items()}
+        obs = {k: v[s] for k, v in self._ring.items()}
+        return obs if self.obs_dtype == "compact" else self._to_reference(obs)
+
+    def _to_reference(self, obs):
+        """Compact device tensors -> the reference's dtypes (copies, on the device)."""
+        dt = torch.float32 if self.kind == "square" else torch.float64
+        out = {k: v.to(dt) for k, v in obs.items()}
+        f = out.get("all_components_feature")
+        if f is not None:  # h*w/(H*W) as the reference divides it (rect:53-71), not float32 widened
+            f[..., 4] = (f[..., 0] * f[..., 1]) / float(self.spec.height * self.spec.width)
+        return out
+
+    @property
+    def single_observation_space(self):
+        """{key: (shape, dtype, low, high)} of one env's observation -- the Box bounds the
+        reference declares (square:56-72, rect:196-230, pin:504-542, spatial:519-575).  A
+        ``gym.spaces.Dict`` is returned instead when gym / gymnasium is importable."""
+        dt = ("float32" if self.kind == "square" else "float64") if self.obs_dtype == "reference" else None
+        desc = {}
+        for k, v in self._ring.items():
+            desc[k] = (tuple(v.shape[2:]), dt or str(v.dtype).replace("torch.", ""), -1.0,
+                       float(max(self.spec.height, self.spec.width, self.spec.max_num_components,
+                                 self.spec.max_pins, 3)))
+        for mod in ("gymnasium", "gym"):
+            try:
+                spaces = __import__(mod).spaces
+                return spaces.Dict({k: spaces.Box(lo, hi, shape=sh, dtype=np.dtype(d))
+                                    for k, (sh, d, lo, hi) in desc.items()})
+            except ImportError:
+                continue
+        return desc
+
+    @property
+    def single_action_space(self):
+        """Sizes of the Tuple(Discrete...) action of one env: (H, W) for the square env,
+        (O, H, W) otherwise (square:44-46, rect:186-194, pin:493-502); the flat Discrete of the
+        wrappers has prod(sizes) actions."""
+        s = self.spec
+        return (s.height, s.width) if self.kind == "square" else (s.n_orient, s.height, s.width)
 
     def reset(self, mask=None):
         """reset() of every env (mask None) or of the envs where ``mask`` is set."""

@@ -155,6 +155,38 @@ def test_fused_small_rollout_against_the_oracle(name):
     env.close()
 
 
+@pytest.mark.parametrize("name", ["A", "B", "C", "D"])
+def test_reference_dtype_mode_equals_the_oracle_value_for_value(name):
+    """obs_dtype="reference": float64 (float32 square) tensors equal to the oracle's arrays
+    without any cast on the comparing side, incl. the exact float64 area ratio."""
+    from ref_harness import make_oracle, pick_action
+
+    cfg = CONFIGS[name]
+    square = cfg["type"] == "square"
+    inst = None if square else draw_instance(cfg, 3)
+    env = make(name, 1, autoreset=False, instances=None if square else [inst], obs_dtype="reference")
+    o = make_oracle(cfg)
+    ref = o.reset() if square else o.reset(instance=inst)
+    got = env.reset()
+    rng = np.random.default_rng(0)
+    for t in range(6):
+        for k, v in ref.items():
+            g = got[k][0].cpu().numpy()
+            v = np.asarray(v)
+            if k == "component_grid":
+                g = g[: v.shape[0]]
+            assert g.dtype == v.dtype and np.array_equal(g, v), (name, t, k)
+        a = pick_action(rng, o.action_mask)
+        ref, _, rd, _ = o.step(a)
+        got, _, _, _ = env.step(torch.tensor([a], dtype=torch.int32, device="cuda"))
+        if rd:
+            break
+    assert env.single_action_space == tuple(o.action_mask.shape)
+    sp = env.single_observation_space
+    assert set(sp.keys() if isinstance(sp, dict) else sp.spaces.keys()) == set(ref.keys())
+    env.close()
+
+
 def test_fused_rollout_is_refused_for_pin_kinds_and_wide_boards():
     for name in ("C", "S_wide_sq", "S_wide_rect"):
         env = make(name, 8)
