@@ -207,6 +207,14 @@ int64_t pcb_launch_count(pcb_env_t* env);
 int pcb_rollout_random(pcb_env_t* env, uint64_t seed, int n_steps, int32_t* d_actions_log,
                        void* stream);
 
+/* The same rollout keeping every step's results for a rollout collector: d_reward_log
+ * [n_steps, N] float64 and d_done_log [n_steps, N] uint8 (device, either may be NULL)
+ * receive reward and done of each step; together with an observation ring of n_steps + 1
+ * slices and d_actions_log this is the whole [T, N, ...] batch a PPO-style learner reads,
+ * produced without a host round trip per step. */
+int pcb_rollout_random_logged(pcb_env_t* env, uint64_t seed, int n_steps, int32_t* d_actions_log,
+                              double* d_reward_log, uint8_t* d_done_log, void* stream);
+
 /* pcb_rollout_random runs the reward kernel of step t concurrently with the step kernel of
  * step t+1 (default on); 0 = strictly one after the other, as pcb_step always does. */
 int pcb_set_reward_overlap(pcb_env_t* env, int on);

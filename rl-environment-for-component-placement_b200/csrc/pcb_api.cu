@@ -738,8 +738,11 @@ int pcb_reset(pcb_env_t* e, const uint8_t* d_reset_mask, void* stream) {
 // overlap = false: step kernel, then the reward kernel, both on `stream`.
 // overlap = true (pcb_rollout_random): the reward kernel of step t runs on the side
 // stream while the step kernel of step t+1 runs on `stream`; step t+2 waits for it.
+// reward_row / done_row != nullptr: this step's reward[N] / done[N] go there instead of the
+// double-buffered result tensors (pcb_rollout_random_logged)
 static int step_impl(pcb_env_t* e, const int32_t* d_actions, int action_format, uint64_t seed,
-                     int32_t* d_next_actions, void* stream, bool overlap) {
+                     int32_t* d_next_actions, void* stream, bool overlap,
+                     double* reward_row = nullptr, uint8_t* done_row = nullptr) {
   int rc = ready(e);
   if (rc) return rc;
   if (!d_actions) return fail(PCB_ERR_INVALID, "d_actions is NULL");
@@ -760,6 +763,8 @@ static int step_impl(pcb_env_t* e, const int32_t* d_actions, int action_format, 
   p.action_format = action_format;
   p.seed = seed;
   p.actions_out = d_next_actions;
+  if (reward_row) p.out.reward = reward_row;
+  if (done_row) p.out.done = done_row;
   rc = launch(e, K_STEP, p, st);
   if (rc) return rc;
   if (routes) {
@@ -917,7 +922,8 @@ int pcb_set_state(pcb_env_t* e, const void* h_state, uint64_t step_no, void* str
 int64_t pcb_launch_count(pcb_env_t* e) { return e ? e->launches : 0; }
 
 // the pin-less kinds: all n_steps in one launch of rollout_small_kernel (pcb_small.cuh)
-static int rollout_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_actions_log, cudaStream_t st) {
+static int rollout_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_actions_log,
+                         double* d_reward_log, uint8_t* d_done_log, cudaStream_t st) {
   CU(cudaSetDevice(e->device));
   RolloutParams p;
   memset(&p, 0, sizeof p);
@@ -925,6 +931,7 @@ static int rollout_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_ac
   p.base = e->base;
   p.state = e->state; p.bank = e->bank; p.ratio_lut = e->ratio_lut; p.stats = e->stats;
   p.actions_log = d_actions_log;
+  p.reward_log = d_reward_log; p.done_log = d_done_log;
   p.seed = seed; p.step_no = e->step_no; p.bank_count = e->bank_count;
   p.n_envs = e->n_envs; p.n_steps = n_steps; p.ring = e->ring; p.slice0 = e->slice;
   cudaEvent_t a = nullptr, b = nullptr;
@@ -951,15 +958,17 @@ static int rollout_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_ac
   return 0;
 }
 
-int pcb_rollout_random(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_actions_log, void* stream) {
+int pcb_rollout_random_logged(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_actions_log,
+                              double* d_reward_log, uint8_t* d_done_log, void* stream) {
   int rc = ready(e);
   if (rc) return rc;
   if (n_steps < 0) return fail(PCB_ERR_INVALID, "n_steps must be >= 0");
   if (n_steps == 0) return 0;
-  if (e->fused) return rollout_fused(e, seed, n_steps, d_actions_log, (cudaStream_t)stream);
-  const size_t per = (size_t)e->n_envs * (e->d.kind == 0 ? 2 : 3);
+  if (e->fused)
+    return rollout_fused(e, seed, n_steps, d_actions_log, d_reward_log, d_done_log, (cudaStream_t)stream);
+  const size_t N = (size_t)e->n_envs, per = N * (e->d.kind == 0 ? 2 : 3);
   // the first action comes from the stand-alone sampler; every step kernel then also
-  // draws the action of the following step (same Philox counter as the sampler would use)
+  // draws the action of the following step (same counter as the sampler would use)
   int32_t* cur = d_actions_log ? d_actions_log : e->d_actions;
   rc = pcb_sample_random_actions(e, seed, cur, stream);
   if (rc) return rc;
@@ -968,11 +977,29 @@ int pcb_rollout_random(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_acti
     if (t + 1 < n_steps)
       nxt = d_actions_log ? d_actions_log + (size_t)(t + 1) * per
                           : (cur == e->d_actions ? e->d_actions2 : e->d_actions);
-    rc = step_impl(e, cur, PCB_ACTION_TUPLE, seed, nxt, stream, e->overlap);
+    rc = step_impl(e, cur, PCB_ACTION_TUPLE, seed, nxt, stream, e->overlap,
+                   d_reward_log ? d_reward_log + (size_t)t * N : nullptr,
+                   d_done_log ? d_done_log + (size_t)t * N : nullptr);
     if (rc) return rc;
     cur = nxt;
   }
-  return join_rewards(e, (cudaStream_t)stream);
+  rc = join_rewards(e, (cudaStream_t)stream);
+  if (rc) return rc;
+  // the result tensors ([2, N], by step parity) still describe the last two steps
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int back = 0; back < 2 && back < n_steps; ++back) {
+    const size_t t = (size_t)(n_steps - 1 - back);
+    const size_t half = (size_t)((e->step_no - 1 - back) & 1) * N;
+    if (d_reward_log)
+      CU(cudaMemcpyAsync(e->base.reward + half, d_reward_log + t * N, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (d_done_log)
+      CU(cudaMemcpyAsync(e->base.done + half, d_done_log + t * N, N, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+int pcb_rollout_random(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_actions_log, void* stream) {
+  return pcb_rollout_random_logged(e, seed, n_steps, d_actions_log, nullptr, nullptr, stream);
 }
 
 int pcb_set_reward_overlap(pcb_env_t* e, int on) {

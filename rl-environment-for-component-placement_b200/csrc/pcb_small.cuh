@@ -31,6 +31,8 @@ struct RolloutParams {
   const float* ratio_lut;
   double* stats;
   int32_t* actions_log;  // nullptr or [n_steps, N, 2|3]
+  double* reward_log;    // nullptr or [n_steps, N]
+  uint8_t* done_log;     // nullptr or [n_steps, N]
   uint64_t seed;
   uint64_t step_no;      // number of the first step
   uint32_t bank_count;
@@ -354,6 +356,9 @@ rollout_small_kernel(const __grid_constant__ RolloutParams p) {
     if (sl == 0 && live) {
       p.base.done[he] = done ? 1 : 0;
       p.base.reward[he] = reward;
+      const size_t le = (size_t)t * N + (size_t)env;
+      if (p.reward_log) p.reward_log[le] = reward;
+      if (p.done_log) p.done_log[le] = done ? 1 : 0;
     }
 
     // ---- observation of slice (slice0 + 1 + t) % ring ----

@@ -30,6 +30,17 @@ class RolloutCollector:
     def collect(self, reset=True):
         env = self.env
         obs = env.reset() if reset or self._step == 0 else env._obs()
+        if self.policy is None and self.zero_copy:
+            # the device random policy needs no host in the loop: one C call for all T steps
+            # (one kernel launch for the pin-less kinds), results logged per step
+            ring = next(iter(env.obs_ring_tensors.values())).shape[0]
+            s0 = env.lib.pcb_current_slice(env._h)
+            env.rollout_random(self.T, self.seed, actions_log=self.actions, reward_log=self.rewards,
+                               done_log=self.dones)
+            self._step += self.T
+            idx = (s0 + torch.arange(self.T + 1, device=env.device)) % ring
+            return {"obs": {k: v[idx] for k, v in env.obs_ring_tensors.items()},
+                    "actions": self.actions, "rewards": self.rewards, "dones": self.dones}
         slices = []
         for t in range(self.T):
             s = env.lib.pcb_current_slice(env._h)

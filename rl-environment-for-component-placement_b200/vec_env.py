@@ -207,12 +207,23 @@ class PcbVecEnv:
             self._h, ctypes.c_uint64(seed), ctypes.c_void_p(out.data_ptr()), self._stream()))
         return out
 
-    def rollout_random(self, n_steps, seed=0, actions_log=None):
+    def rollout_random(self, n_steps, seed=0, actions_log=None, reward_log=None, done_log=None):
         """n_steps of {device random policy; step} from one C call (simulate() of
-        agent/random/*.py).  actions_log: optional int32 [n_steps, N, k] device tensor."""
-        ptr = None if actions_log is None else ctypes.c_void_p(actions_log.data_ptr())
-        self._check(self.lib.pcb_rollout_random(self._h, ctypes.c_uint64(seed), int(n_steps), ptr,
-                                               self._stream()))
+        agent/random/*.py).  Optional device logs: actions_log int32 [n_steps, N, k],
+        reward_log float64 [n_steps, N], done_log uint8 [n_steps, N]."""
+        def ptr(t, dtype, shape):
+            if t is None:
+                return None
+            if t.dtype != dtype or tuple(t.shape) != shape or not t.is_contiguous() or not t.is_cuda:
+                raise ValueError(f"log tensor must be a contiguous cuda {dtype} tensor of shape {shape}")
+            return ctypes.c_void_p(t.data_ptr())
+
+        T, N = int(n_steps), self.num_envs
+        self._check(self.lib.pcb_rollout_random_logged(
+            self._h, ctypes.c_uint64(seed), T,
+            ptr(actions_log, torch.int32, (T, N, self.spec.action_width)),
+            ptr(reward_log, torch.float64, (T, N)), ptr(done_log, torch.uint8, (T, N)),
+            self._stream()))
 
     def reward_overlap(self, on):
         """rollout_random: run the reward kernel of step t alongside the step kernel of t+1."""

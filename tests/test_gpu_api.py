@@ -267,6 +267,37 @@ def test_rollout_collector_zero_copy_ring():
     env.close()
 
 
+@pytest.mark.parametrize("name", ["B", "C", "C_both", "D", "A"])
+def test_logged_rollout_equals_stepping_by_hand(name):
+    """RolloutCollector without a policy = one pcb_rollout_random_logged call (one launch for
+    the pin-less kinds): observations, actions, rewards and dones of every step must equal
+    a hand-written {sample; step} loop, and results() must describe the last step."""
+    import pcbgpu
+
+    N, T = 300, 13
+    a, b = make(name, N, obs_ring=T + 1, seed=4), make(name, N, obs_ring=T + 1, seed=4)
+    col = pcbgpu.RolloutCollector(a, horizon=T, seed=6)
+    assert col.zero_copy
+    for rep in range(2):  # the second collect continues the episodes and wraps the ring
+        out = col.collect(reset=(rep == 0))
+        obs = b.reset() if rep == 0 else b._obs()
+        for t in range(T):
+            for k, v in obs.items():
+                assert torch.equal(out["obs"][k][t], v), (name, rep, t, k)
+            act = b.sample_random_actions(seed=6)
+            assert torch.equal(out["actions"][t], act), (name, rep, t)
+            obs, r, d, _ = b.step(act)
+            assert torch.equal(out["rewards"][t], r) and torch.equal(out["dones"][t], d), (name, rep, t)
+        for k, v in obs.items():
+            assert torch.equal(out["obs"][k][T], v), (name, rep, "last", k)
+        ra, rb = a.results(), b.results()
+        for k in ("reward", "done"):
+            assert torch.equal(ra[k], rb[k]), (name, rep, k)
+    sa, sb = a.episode_stats(), b.episode_stats()
+    assert sa["episodes"] == sb["episodes"] > 0 and sa["sum_length"] == sb["sum_length"]
+    a.close(); b.close()
+
+
 def test_errors_are_loud():
     import pcbgpu
     from pcbgpu._lib import PcbError
