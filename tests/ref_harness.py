@@ -185,3 +185,8 @@ CONFIGS["REF_rect"] = dict(type="rectangle", height=10, width=10, min_component_
                            min_component_h=2, max_component_w=4, max_component_h=4,
                            max_num_components=20, min_num_components=20)
 CONFIGS["REF_square"] = dict(type="square", height=10, width=10, component_n=2)
+# many small components on a small board: more component rows than lanes per env in the
+# multi-env-per-warp rollout kernel (8 lanes per env, 20 rows)
+CONFIGS["S_rect_many"] = dict(type="rectangle", height=8, width=8, min_component_w=1,
+                              max_component_w=2, min_component_h=1, max_component_h=2,
+                              max_num_components=20, min_num_components=17)

@@ -76,7 +76,7 @@ def test_fused_rollout_equals_sample_then_step(name):
     a.close(); b.close()
 
 
-SMALL = ["A", "A2", "B", "S_sq", "S_rect", "S_rect_full", "REF_rect", "REF_square"]
+SMALL = ["A", "A2", "B", "S_sq", "S_rect", "S_rect_full", "S_rect_many", "REF_rect", "REF_square"]
 
 
 @pytest.mark.parametrize("autoreset", [True, False])
@@ -116,7 +116,7 @@ def test_fused_small_rollout_is_bit_identical_to_per_step_launches(name, autores
     a.close(); b.close()
 
 
-@pytest.mark.parametrize("name", ["A", "B", "S_rect", "S_sq", "REF_rect"])
+@pytest.mark.parametrize("name", ["A", "B", "S_rect", "S_sq", "REF_rect", "S_rect_many"])
 def test_fused_small_rollout_against_the_oracle(name):
     """The logged actions of a fused rollout replayed through the oracle: every
     observation of every step (ring of T+1 slices) must be the oracle's."""

@@ -13,7 +13,7 @@ def test_square(name):
     run_parity(name, range(16, 32), p_invalid=0.3)
 
 
-@pytest.mark.parametrize("name", ["B", "S_rect", "S_rect_full"])
+@pytest.mark.parametrize("name", ["B", "S_rect", "S_rect_full", "S_rect_many"])
 def test_rect(name):
     run_parity(name, range(64), extra_steps=2)
     run_parity(name, range(64, 96), p_invalid=0.2)

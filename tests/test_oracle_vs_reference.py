@@ -64,7 +64,7 @@ def test_square(name):
     run_pair(name, range(20, 30), p_invalid=0.3)
 
 
-@pytest.mark.parametrize("name", ["B", "S_rect", "S_rect_full"])
+@pytest.mark.parametrize("name", ["B", "S_rect", "S_rect_full", "S_rect_many"])
 def test_rect(name):
     run_pair(name, range(40))
     run_pair(name, range(40, 60), p_invalid=0.2)
