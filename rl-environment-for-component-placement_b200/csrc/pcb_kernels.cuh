@@ -29,7 +29,7 @@ constexpr unsigned kFull = 0xffffffffu;
 #define PCB_LAYOUT_FIELDS(X)                                                                   \
   X(O) X(P) X(F) X(st_comps) X(st_pins) X(st_occ) X(st_stride) X(rec_comps) X(rec_pins)        \
   X(rec_stride) X(grid_b) X(mask_b) X(feat_n) X(pnum_n) X(pcat_n) X(pgrid_b) X(cgrid_b)        \
-  X(sm_mrow) X(sm_stage) X(sm_scr) X(sm_stride)
+  X(sm_mrow) X(sm_stage) X(sm_scr) X(sm_stride) X(pchunk)
 
 template <int KIND, int HH, int WW, int CC, int MH, int MW, int KK, int MAXPINS>
 struct FixedShape {
@@ -636,15 +636,17 @@ __device__ __forceinline__ void write_obs(const S& sh, const Params& p, Env<T>& 
   // and leave the SM as full coalesced chunks: scattered 2..8-byte stores each occupy a
   // request slot on the SM -> L2 path, which is the busiest unit of this kernel.
   const int pnum_n = sh.pnum_n(), pcat_n = sh.pcat_n();
-  const int pins_bytes = ((pnum_n + pcat_n) * 2 + 15) & ~15;
+  // pin env: rows of `pchunk` components per pass (all of them unless the configuration is large)
+  const int pchunk = sh.pchunk();
+  const int pins_bytes = kind == 2 ? ((pchunk * sh.P() * 10 + 15) & ~15) : (((pnum_n + pcat_n) * 2 + 15) & ~15);
   int16_t* snum = reinterpret_cast<int16_t*>(e.stage);
-  int16_t* scat = snum + pnum_n;
+  int16_t* scat = snum + (kind == 2 ? pchunk * sh.P() * 4 : pnum_n);
   float* fdst = reinterpret_cast<float*>(e.stage + pins_bytes);
   float* feat = p.out.feat + (size_t)env * sh.feat_n();
 
   // phase A: zero the pin area; all_components_feature = [h, w, x|-1, y|-1, h*w/(H*W)]
   // (+ pin ids of the component padded with -1, spatial)
-  if (kind >= 2) zero_smem(e.stage, pins_bytes, lane);
+  if (kind == 3) zero_smem(e.stage, pins_bytes, lane);
   if (kind != 3) {
     for (int c = lane; c < C; c += 32) {  // one lane per component row (5 floats)
       float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f, f4 = 0.f;
@@ -692,25 +694,49 @@ __device__ __forceinline__ void write_obs(const S& sh, const Params& p, Env<T>& 
 
   // phase B: every winning pin writes its feature row (pin:1521-1542, spatial:1469-1485);
   // the spatial env also lists each component's pin ids in its feature row
-  if (kind >= 2) {
+  if (kind == 2) {
+    const int P = sh.P();
+    copy_out(feat, fdst, sh.feat_n() * 4, lane);
+    for (int c0 = 0; c0 < C; c0 += pchunk) {
+      const int nc = min(pchunk, C - c0), rows = nc * P;
+      zero_smem(e.stage, pins_bytes, lane);
+      __syncwarp();
+      for (int q = lane; q < n_pins; q += 32) {
+        PinRec pr = e.pins[q];
+        const int c = pr.comp - c0;
+        if (!(pr.flags & kPinWinner) || (unsigned)c >= (unsigned)nc) continue;
+        CompRec r = e.comps[pr.comp];
+        int ax = r.x == 0xFF ? -1 : r.x + pr.rx;
+        int ay = r.x == 0xFF ? -1 : r.y + pr.ry;
+        const int row = c * P + pr.pin_id;
+        // [rel_x, rel_y, abs_x, abs_y] as int16
+        uint2 v = make_uint2((uint32_t)pr.rx | ((uint32_t)pr.ry << 16),
+                             ((uint32_t)ax & 0xffffu) | ((uint32_t)ay << 16));
+        *reinterpret_cast<uint2*>(snum + row * 4) = v;
+        scat[row] = pr.net;
+      }
+      __syncwarp();
+      copy_out(p.out.pnum + (size_t)env * pnum_n + c0 * P * 4, snum, rows * 8, lane);
+      copy_out(p.out.pcat + (size_t)env * pcat_n + c0 * P, scat, rows * 2, lane);
+      __syncwarp();
+    }
+    return;
+  }
+  if (kind == 3) {
     for (int q = lane; q < n_pins; q += 32) {
       PinRec pr = e.pins[q];
-      if (kind == 3) fdst[pr.comp * F + 5 + pr.rank] = (float)pr.pin_id;
+      fdst[pr.comp * F + 5 + pr.rank] = (float)pr.pin_id;
       if (!(pr.flags & kPinWinner)) continue;
       CompRec r = e.comps[pr.comp];
       int ax = r.x == 0xFF ? -1 : r.x + pr.rx;
       int ay = r.x == 0xFF ? -1 : r.y + pr.ry;
-      int row = kind == 3 ? pr.pin_id : pr.comp * sh.P() + pr.pin_id;
-      // [rel_x, rel_y, abs_x, abs_y] as int16
+      const int row = pr.pin_id;
       uint2 v = make_uint2((uint32_t)pr.rx | ((uint32_t)pr.ry << 16),
                            ((uint32_t)ax & 0xffffu) | ((uint32_t)ay << 16));
       *reinterpret_cast<uint2*>(snum + row * 4) = v;
-      if (kind == 3)
-        *reinterpret_cast<uint32_t*>(scat + row * 2) = (uint32_t)pr.net | ((uint32_t)pr.comp << 16);
-      else
-        scat[row] = pr.net;
+      *reinterpret_cast<uint32_t*>(scat + row * 2) = (uint32_t)pr.net | ((uint32_t)pr.comp << 16);
     }
-    if (kind == 3 && lane == 0) { scat[pcat_n - 2] = -1; scat[pcat_n - 1] = -1; }
+    if (lane == 0) { scat[pcat_n - 2] = -1; scat[pcat_n - 1] = -1; }
     __syncwarp();
   }
 

@@ -84,6 +84,7 @@ struct Layout {
   int rec_comps, rec_pins, rec_stride;
   int grid_b, mask_b, feat_n, pnum_n, pcat_n, pgrid_b, cgrid_b;
   int sm_mrow, sm_stage, sm_scr, sm_stride;
+  int pchunk;  // pin env: components whose pin feature rows are staged per pass
 };
 
 PCB_HD constexpr int align16c(int v) { return (v + 15) & ~15; }
@@ -92,6 +93,15 @@ PCB_HD constexpr int maxc(int a, int b) { return a > b ? a : b; }
 // terminal-reward scratch per warp: per-pin arrays + per-net arrays + pair queue
 PCB_HD constexpr int route_scratch_bytes(int max_pins, int K) {
   return max_pins * (8 + 8 + 8 + 8 + 2 + 2 + 2 + 1) + K * (8 + 8 + 2 + 2) + 2 + kPairQueue * 4 + 64;
+}
+
+// Pin env: the pin feature rows (C * P rows of 10 bytes) are staged in shared memory in passes
+// of `pchunk` components, so that a large configuration (E: 5 KB of rows) does not set the
+// CTAs per SM; a multiple of 8 components keeps every pass 16-byte aligned in the output.
+PCB_HD constexpr int pin_chunk_comps(int C, int P) {
+  if (C * P * 10 <= 3584) return C;
+  const int by_size = 8 * maxc(1, 2048 / (P * 80));
+  return by_size < C ? by_size : C;
 }
 
 // fast_board: the kernel expands bitboards straight from registers (FixedShape 16/32/64
@@ -119,7 +129,9 @@ PCB_HD constexpr Layout make_layout(int kind, int H, int W, int C, int mh, int m
   L.pgrid_b = kind == 3 ? H * W * K : 0;
   L.cgrid_b = kind == 3 ? C * mh * mw * K : 0;
   // staging: pin feature rows + component features side by side; the spatial boards reuse it
-  int stage = align16c((L.pnum_n + L.pcat_n) * 2) + align16c(L.feat_n * 4) + 16;
+  L.pchunk = kind == 2 ? pin_chunk_comps(C, L.P) : C;
+  const int pins_area = kind == 2 ? L.pchunk * L.P * 10 : (L.pnum_n + L.pcat_n) * 2;
+  int stage = align16c(pins_area) + align16c(L.feat_n * 4) + 16;
   // pin_grid is staged in two halves of the rows
   if (kind == 3) stage = maxc(stage, maxc(align16c(((H + 1) / 2) * W * K), L.cgrid_b));
   L.sm_mrow = L.st_stride;
