@@ -123,3 +123,44 @@ def run_parity(name, seeds, autoreset=False, p_invalid=0.0, episodes=1, extra_st
         stats["reward_inexact"] = stats.get("reward_inexact", 0) + inexact
     env.close()
     return n_steps
+
+
+def run_rollout_parity(name, N=24, T=30, episodes=12, seed=5):
+    """pcb_rollout_random (one launch of rollout_small_kernel for the pin-less kinds) against
+    the oracle: the logged actions are replayed through oracle envs and every observation of
+    every step (ring of T+1 slices), the per-step rewards / dones and the episode count must
+    agree.  Returns the number of env-steps compared."""
+    import pcbgpu
+
+    cfg = CONFIGS[name]
+    square = cfg["type"] == "square"
+    insts = None if square else [draw_instance(cfg, s + k * 100003) for k in range(episodes)
+                                 for s in range(N)]
+    env = pcbgpu.PcbVecEnv(cfg, N, autoreset=True, instances=insts, obs_ring=T + 1)
+    env.reset()
+    log = torch.zeros((T, N, env.spec.action_width), dtype=torch.int32, device="cuda")
+    rlog = torch.zeros((T, N), dtype=torch.float64, device="cuda")
+    dlog = torch.zeros((T, N), dtype=torch.uint8, device="cuda")
+    env.rollout_random(T, seed=seed, actions_log=log, reward_log=rlog, done_log=dlog)
+    torch.cuda.synchronize()
+    acts, rews, dones = log.cpu().numpy(), rlog.cpu().numpy(), dlog.cpu().numpy()
+    ring = env.obs_ring_tensors
+    C = env.spec.max_num_components
+    n_done = 0
+    for i in range(N):
+        o = make_oracle(cfg)
+        o.reset() if square else o.reset(instance=insts[i])
+        epi = 0
+        for t in range(T):
+            ro, rr, rd, _ = o.step(tuple(int(v) for v in acts[t, i]))
+            assert float_close(float(rews[t, i]), float(rr)), (name, i, t, rews[t, i], rr)
+            assert bool(dones[t, i]) == rd, (name, i, t, "done")
+            if rd:
+                epi += 1
+                n_done += 1
+                ro = o.reset() if square else o.reset(instance=insts[(epi * N + i) % len(insts)])
+            compare_obs({k: v[t + 1] for k, v in ring.items()}, i, ro, C, (name, i, t))
+    st = env.episode_stats()
+    assert st["episodes"] == n_done > 0, (st, n_done)
+    env.close()
+    return N * T

@@ -120,39 +120,9 @@ def test_fused_small_rollout_is_bit_identical_to_per_step_launches(name, autores
 def test_fused_small_rollout_against_the_oracle(name):
     """The logged actions of a fused rollout replayed through the oracle: every
     observation of every step (ring of T+1 slices) must be the oracle's."""
-    from parity import compare_obs
-    from ref_harness import make_oracle
+    from parity import run_rollout_parity
 
-    cfg = CONFIGS[name]
-    square = cfg["type"] == "square"
-    N, T, episodes = 24, 30, 12
-    insts = None if square else [draw_instance(cfg, s + k * 100003) for k in range(episodes)
-                                 for s in range(N)]
-    env = make(name, N, autoreset=True, instances=insts, obs_ring=T + 1)
-    assert env.fused_rollout(True)
-    env.reset()
-    log = torch.zeros((T, N, env.spec.action_width), dtype=torch.int32, device="cuda")
-    env.rollout_random(T, seed=5, actions_log=log)
-    torch.cuda.synchronize()
-    acts = log.cpu().numpy()
-    ring = env.obs_ring_tensors
-    C = env.spec.max_num_components
-    n_done = 0
-    for i in range(N):
-        o = make_oracle(cfg)
-        o.reset() if square else o.reset(instance=insts[i])
-        epi = 0
-        for t in range(T):
-            ro, rr, rd, _ = o.step(tuple(int(v) for v in acts[t, i]))
-            assert rr == 1.0, (name, i, t, "the random policy only picks valid actions")
-            if rd:
-                epi += 1
-                n_done += 1
-                ro = o.reset() if square else o.reset(instance=insts[(epi * N + i) % len(insts)])
-            compare_obs({k: v[t + 1] for k, v in ring.items()}, i, ro, C, (name, i, t))
-    st = env.episode_stats()
-    assert st["episodes"] == n_done > 0
-    env.close()
+    assert run_rollout_parity(name) > 0
 
 
 @pytest.mark.parametrize("name", ["A", "B", "C", "D"])
