@@ -222,8 +222,9 @@ int pcb_set_reward_overlap(pcb_env_t* env, int on);
 /* The pin-less kinds (square, rectangle; H, W <= 32) run pcb_rollout_random as ONE launch
  * of a multi-step kernel that keeps the state on chip and packs 32/LPE environments into a
  * warp (LPE = 8, 16, 32 lanes >= H) -- default on; the result is bit-identical to n_steps x
- * { pcb_sample_random_actions; pcb_step }.  pcb_set_fused_rollout(env, 0) selects the
- * per-step launches instead; returns 1 when the fused kernel will be used, 0 when not
+ * { pcb_sample_random_actions; pcb_step }; pcb_step itself runs one step of the same kernel
+ * with the caller's actions.  pcb_set_fused_rollout(env, 0) selects the one-warp-per-env
+ * kernels and per-step launches instead; returns 1 when the fused kernel will be used, 0 when not
  * (pin kinds, boards wider than 32), negative on error.  pcb_fused_rollout_times: device
  * time [ms], launches and steps of the fused kernel since the last call (needs
  * pcb_enable_kernel_timing). */

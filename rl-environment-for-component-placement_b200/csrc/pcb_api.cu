@@ -738,6 +738,10 @@ int pcb_reset(pcb_env_t* e, const uint8_t* d_reset_mask, void* stream) {
 // overlap = false: step kernel, then the reward kernel, both on `stream`.
 // overlap = true (pcb_rollout_random): the reward kernel of step t runs on the side
 // stream while the step kernel of step t+1 runs on `stream`; step t+2 waits for it.
+static int rollout_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_actions_log,
+                         double* d_reward_log, uint8_t* d_done_log, cudaStream_t st,
+                         const int32_t* d_actions, int action_format);
+
 // reward_row / done_row != nullptr: this step's reward[N] / done[N] go there instead of the
 // double-buffered result tensors (pcb_rollout_random_logged)
 static int step_impl(pcb_env_t* e, const int32_t* d_actions, int action_format, uint64_t seed,
@@ -750,6 +754,8 @@ static int step_impl(pcb_env_t* e, const int32_t* d_actions, int action_format, 
     return fail(PCB_ERR_INVALID, "unknown action format %d", action_format);
   CU(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream;
+  if (e->fused && !d_next_actions)  // pin-less kinds: the multi-env-per-warp kernel, one step
+    return rollout_fused(e, seed, 1, nullptr, reward_row, done_row, st, d_actions, action_format);
   const bool routes = e->d.kind >= 2;
   const int par = (int)(e->step_no & 1);
   // the reward kernel of step t-2 used the same job buffer / scalar half
@@ -922,14 +928,17 @@ int pcb_set_state(pcb_env_t* e, const void* h_state, uint64_t step_no, void* str
 int64_t pcb_launch_count(pcb_env_t* e) { return e ? e->launches : 0; }
 
 // the pin-less kinds: all n_steps in one launch of rollout_small_kernel (pcb_small.cuh)
+// d_actions != nullptr: one step with the caller's actions (pcb_step) in the same kernel.
 static int rollout_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_actions_log,
-                         double* d_reward_log, uint8_t* d_done_log, cudaStream_t st) {
+                         double* d_reward_log, uint8_t* d_done_log, cudaStream_t st,
+                         const int32_t* d_actions, int action_format) {
   CU(cudaSetDevice(e->device));
   RolloutParams p;
   memset(&p, 0, sizeof p);
   p.d = e->d;
   p.base = e->base;
   p.state = e->state; p.bank = e->bank; p.ratio_lut = e->ratio_lut; p.stats = e->stats;
+  p.actions = d_actions; p.action_format = action_format;
   p.actions_log = d_actions_log;
   p.reward_log = d_reward_log; p.done_log = d_done_log;
   p.seed = seed; p.step_no = e->step_no; p.bank_count = e->bank_count;
@@ -965,7 +974,8 @@ int pcb_rollout_random_logged(pcb_env_t* e, uint64_t seed, int n_steps, int32_t*
   if (n_steps < 0) return fail(PCB_ERR_INVALID, "n_steps must be >= 0");
   if (n_steps == 0) return 0;
   if (e->fused)
-    return rollout_fused(e, seed, n_steps, d_actions_log, d_reward_log, d_done_log, (cudaStream_t)stream);
+    return rollout_fused(e, seed, n_steps, d_actions_log, d_reward_log, d_done_log, (cudaStream_t)stream,
+                         nullptr, 0);
   const size_t N = (size_t)e->n_envs, per = N * (e->d.kind == 0 ? 2 : 3);
   // the first action comes from the stand-alone sampler; every step kernel then also
   // draws the action of the following step (same counter as the sampler would use)

@@ -30,6 +30,8 @@ struct RolloutParams {
   const uint8_t* bank;
   const float* ratio_lut;
   double* stats;
+  const int32_t* actions;  // nullptr: the device random policy; else the actions of the one
+  int action_format;       // step to run (pcb_step): [N, 2|3] tuples or [N] flat indices
   int32_t* actions_log;  // nullptr or [n_steps, N, 2|3]
   double* reward_log;    // nullptr or [n_steps, N]
   uint8_t* done_log;     // nullptr or [n_steps, N]
@@ -269,26 +271,52 @@ rollout_small_kernel(const __grid_constant__ RolloutParams p) {
     const uint64_t step_no = p.step_no + (uint64_t)t;
     const uint32_t he = ((uint32_t)step_no & 1u) ? N + (uint32_t)env : (uint32_t)env;
 
-    // ---- random policy; its pick is valid exactly when the mask has a set bit, and with
-    // an empty mask it reports (0,0,0), whose mask bit is 0: validate_action == `any` ----
-    int o, x, y;
-    sample_action_g<LPE, S>(sh, m0, m1, p.seed, env, step_no, lane, o, x, y);
-    if (p.actions_log && sl == 0 && live) {
-      int32_t* a = p.actions_log + ((size_t)t * N + (size_t)env) * aw;
-      if (kind == 0) { a[0] = x; a[1] = y; }
-      else { a[0] = o; a[1] = x; a[2] = y; }
-    }
-    const bool valid = any;
-    if (valid) {  // update_grid (square:175-185, rect:459-484); no sync inside
-      int ph = d.sq_n, pw = d.sq_n;
+    int o = 0, x = 0, y = 0, ph = d.sq_n, pw = d.sq_n;
+    bool valid;
+    if (p.actions) {
+      // ---- given actions (pcb_step; FlatteningActionWrapper*: env_wrappers.py:80-98,
+      // wrapper_square.py:54-69).  validate_action == mask bit, recomputed (square:155-173,
+      // rect:434-457); actions outside the box are invalid ----
+      if (p.action_format == 1) {
+        const int a = p.actions[env];
+        if (a < 0) { o = -1; }
+        else { o = a / HW; const int rem = a - o * HW; x = rem / W; y = rem - x * W; }
+      } else if (kind == 0) {
+        x = p.actions[2 * env]; y = p.actions[2 * env + 1];
+      } else {
+        o = p.actions[3 * env]; x = p.actions[3 * env + 1]; y = p.actions[3 * env + 2];
+      }
+      bool in_range = (unsigned)o < (unsigned)O && (unsigned)x < (unsigned)H && (unsigned)y < (unsigned)W;
       if (kind != 0) {
+        in_range = in_range && cur < n_comp;
+        const uint32_t r = comps[in_range ? cur : 0];
+        const int ch = r & 0xff, cw = (r >> 8) & 0xff;
+        ph = (o & 1) ? cw : ch;
+        pw = (o & 1) ? ch : cw;
+      }
+      const bool fits = in_range && x + ph <= H && y + pw <= W;
+      const uint32_t cols = fits ? (low_mask<uint32_t>(pw) << y) : 0u;
+      const bool clash = group_any<LPE>(sl >= x && sl < x + ph && (occ & cols), gmask);
+      valid = fits && !clash;
+    } else {
+      // ---- random policy; its pick is valid exactly when the mask has a set bit, and with
+      // an empty mask it reports (0,0,0), whose mask bit is 0: validate_action == `any` ----
+      sample_action_g<LPE, S>(sh, m0, m1, p.seed, env, step_no, lane, o, x, y);
+      valid = any;
+      if (kind != 0 && valid) {
         const uint32_t r = comps[cur];
         const int ch = r & 0xff, cw = (r >> 8) & 0xff;
         ph = (o & 1) ? cw : ch;
         pw = (o & 1) ? ch : cw;
       }
-      if (sl >= x && sl < x + ph) occ |= low_mask<uint32_t>(pw) << y;
     }
+    if (p.actions_log && sl == 0 && live) {
+      int32_t* a = p.actions_log + ((size_t)t * N + (size_t)env) * aw;
+      if (kind == 0) { a[0] = x; a[1] = y; }
+      else { a[0] = o; a[1] = x; a[2] = y; }
+    }
+    // update_grid (square:175-185, rect:459-484)
+    if (valid && sl >= x && sl < x + ph) occ |= low_mask<uint32_t>(pw) << y;
     __syncwarp();  // every lane has read comps[cur]
     if (valid && kind != 0) {
       if (sl == 0) comps[cur] = (comps[cur] & 0xffffu) | ((uint32_t)x << 16) | ((uint32_t)y << 24);

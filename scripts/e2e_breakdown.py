@@ -1,4 +1,4 @@
-"""Where the end-to-end step time goes (config C, 65 536 envs): device step with a sync per
+"""Where the end-to-end step time goes (default config C, 65 536 envs; argv: workload envs): device step with a sync per
 step, + H2D of the actions, + D2H of reward/done, and the full pcb_step_host."""
 import os
 import sys
@@ -15,13 +15,18 @@ ge.build()
 import pcbgpu  # noqa: E402
 from ref_harness import CONFIGS  # noqa: E402
 
-N, K = 65536, 200
-env = pcbgpu.PcbVecEnv(CONFIGS["C"], N, autoreset=True, obs_ring=4, bank_size=4 * N, seed=1,
+NAME = sys.argv[1] if len(sys.argv) > 1 else "C"
+N, K = int(sys.argv[2]) if len(sys.argv) > 2 else 65536, 200
+env = pcbgpu.PcbVecEnv(CONFIGS[NAME], N, autoreset=True, obs_ring=4, bank_size=4 * N, seed=1,
                        generate_on_device=True)
 env.reset()
-log = torch.zeros((K, N, 3), dtype=torch.int32, device="cuda")
+H_, W_, AW = env.spec.height, env.spec.width, env.spec.action_width
+log = torch.zeros((K, N, AW), dtype=torch.int32, device="cuda")
 env.rollout_random(K, seed=3, actions_log=log)
-flat = ((log[..., 0] * 32 + log[..., 1]) * 32 + log[..., 2]).int().contiguous()
+if AW == 3:
+    flat = ((log[..., 0] * H_ + log[..., 1]) * W_ + log[..., 2]).int().contiguous()
+else:
+    flat = (log[..., 0] * W_ + log[..., 1]).int().contiguous()
 h_act = torch.empty((K, N), dtype=torch.int32, pin_memory=True)
 h_act.copy_(flat)
 h_r = torch.empty((N,), dtype=torch.float64, pin_memory=True)
@@ -72,6 +77,8 @@ def no_sync(t):
     env.step_async(flat[t])
 
 
+if os.environ.get("NO_FUSED"):
+    env.fused_rollout(False)
 run("pcb_step, device actions, no sync", no_sync)
 run("pcb_step, device actions, sync every step", dev_only)
 run("+ H2D of the actions (torch copy)", with_h2d)
