@@ -21,7 +21,32 @@ ap.add_argument("--iters", type=int, default=5)
 ap.add_argument("--horizon", type=int, default=16)
 args = ap.parse_args()
 env = pcbgpu.PcbVecEnv(CONFIGS["D"], args.envs, autoreset=True, bank_size=args.envs * 8, seed=1)
+import time  # noqa: E402
+
+import torch  # noqa: E402
+
 trainer = PPOTrainer(env, horizon=args.horizon)
-for i, rec in enumerate(trainer.train(args.iters)):
-    print(f"iter {i}: loss {rec['loss']:.4f}  episodes {rec['episodes']:.0f}  "
-          f"mean return {rec['mean_return']:.4f}")
+for i in range(args.iters):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    batch = trainer.collect()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    loss = trainer.update(batch)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    st = env.episode_stats(reset=True)
+    n = args.envs * args.horizon
+    print(f"iter {i}: loss {loss:.4f}  episodes {st['episodes']:.0f}  "
+          f"mean return {st['sum_return'] / max(st['episodes'], 1.0):.4f}  "
+          f"collect {n / (t1 - t0):.3e} env-steps/s (policy forward + env step)  "
+          f"update {t2 - t1:.3f} s")
+# the env's share of a collection step: the same steps with the actions replayed, no policy
+acts = batch["actions"].int()
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for t in range(args.horizon):
+    env.step(acts[t])
+torch.cuda.synchronize()
+print(f"env only: {args.envs * args.horizon / (time.perf_counter() - t0):.3e} env-steps/s "
+      f"(pcb_step per step, flat actions decoded in the kernel)")
