@@ -72,6 +72,12 @@ class PcbVecEnv:
                                        ctypes.byref(self._h)))
         self._ring = {k: _lib.tensor(self._h, k, self.lib) for k in OBS_KEYS[self.kind]}
         self._res = {k: _lib.tensor(self._h, k, self.lib) for k in RESULT_KEYS}
+        # per-slice / per-half view dicts are built once: indexing a tensor costs ~1 us per key
+        # on the host, which is what a step of a small batch costs on the device
+        self._obs_views = {}
+        self._res_views = [{k: v[h] for k, v in self._res.items()} for h in (0, 1)]
+        self._info_views = [{k: r[k] for k in ("wirelength", "num_intersections", "episode_return",
+                                               "episode_length")} for r in self._res_views]
         self._actions = torch.zeros((self.num_envs, self.spec.action_width), dtype=torch.int32,
                                     device=self.device)
         if self.kind != "square":
@@ -86,7 +92,7 @@ class PcbVecEnv:
     # -- lifecycle -----------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
-            self._ring, self._res = {}, {}
+            self._ring, self._res, self._obs_views, self._res_views, self._info_views = {}, {}, {}, [], []
             self.lib.pcb_destroy(self._h)
             self._h = None
 
@@ -123,8 +129,10 @@ class PcbVecEnv:
     # -- gym surface ---------------------------------------------------------
     def _obs(self):
         s = self.lib.pcb_current_slice(self._h)
-        obs = {k: v[s] for k, v in self._ring.items()}
-        return obs if self.obs_dtype == "compact" else self._to_reference(obs)
+        obs = self._obs_views.get(s)
+        if obs is None:
+            obs = self._obs_views[s] = {k: v[s] for k, v in self._ring.items()}
+        return dict(obs) if self.obs_dtype == "compact" else self._to_reference(obs)
 
     def _to_reference(self, obs):
         """Compact device tensors -> the reference's dtypes (copies, on the device)."""
@@ -173,9 +181,9 @@ class PcbVecEnv:
         return self._obs()
 
     def step_async(self, actions):
-        a = torch.as_tensor(actions, device=self.device)
-        if a.dtype != torch.int32 or not a.is_contiguous():
-            a = a.to(torch.int32).contiguous()
+        a = actions
+        if not (isinstance(a, torch.Tensor) and a.is_cuda and a.dtype == torch.int32 and a.is_contiguous()):
+            a = torch.as_tensor(actions, device=self.device).to(torch.int32).contiguous()
         if a.dim() == 1:
             if a.numel() != self.num_envs:
                 raise ValueError("flat actions must have shape [num_envs]")
@@ -190,15 +198,13 @@ class PcbVecEnv:
 
     def results(self):
         """reward, done and the info tensors of the step that just ran ([N] views)."""
-        h = self.lib.pcb_current_result_half(self._h)
-        return {k: v[h] for k, v in self._res.items()}
+        return dict(self._res_views[self.lib.pcb_current_result_half(self._h)])
 
     def step(self, actions):
         self.step_async(actions)
-        r = self.results()
-        info = {k: r[k] for k in ("wirelength", "num_intersections", "episode_return",
-                                  "episode_length")}
-        return self._obs(), r["reward"], r["done"], info
+        h = self.lib.pcb_current_result_half(self._h)
+        r = self._res_views[h]
+        return self._obs(), r["reward"], r["done"], dict(self._info_views[h])
 
     def sample_random_actions(self, seed=0, out=None):
         """agent/random/random_policy_*.py on device: uniform over the valid actions."""
