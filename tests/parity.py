@@ -125,7 +125,7 @@ def run_parity(name, seeds, autoreset=False, p_invalid=0.0, episodes=1, extra_st
     return n_steps
 
 
-def run_rollout_parity(name, N=24, T=30, episodes=12, seed=5):
+def run_rollout_parity(name, N=24, T=30, episodes=12, seed=5, expect_done=True):
     """pcb_rollout_random (one launch of rollout_small_kernel for the pin-less kinds) against
     the oracle: the logged actions are replayed through oracle envs and every observation of
     every step (ring of T+1 slices), the per-step rewards / dones and the episode count must
@@ -161,6 +161,6 @@ def run_rollout_parity(name, N=24, T=30, episodes=12, seed=5):
                 ro = o.reset() if square else o.reset(instance=insts[(epi * N + i) % len(insts)])
             compare_obs({k: v[t + 1] for k, v in ring.items()}, i, ro, C, (name, i, t))
     st = env.episode_stats()
-    assert st["episodes"] == n_done > 0, (st, n_done)
+    assert st["episodes"] == n_done and (n_done > 0 or not expect_done), (st, n_done)
     env.close()
     return N * T

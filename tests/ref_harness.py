@@ -190,3 +190,8 @@ CONFIGS["REF_square"] = dict(type="square", height=10, width=10, component_n=2)
 CONFIGS["S_rect_many"] = dict(type="rectangle", height=8, width=8, min_component_w=1,
                               max_component_w=2, min_component_h=1, max_component_h=2,
                               max_num_components=20, min_num_components=17)
+
+# random configurations accepted by the reference (tests/golden/make_fuzz_configs.py)
+from fuzz_configs import FUZZ  # noqa: E402
+
+CONFIGS.update(FUZZ)

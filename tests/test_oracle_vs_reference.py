@@ -100,3 +100,16 @@ def test_wide_square():
 @pytest.mark.parametrize("name", ["REF_spatial", "REF_rect", "REF_square"])
 def test_reference_shipped_configs(name):
     run_pair(name, range(20), extra_steps=2)
+
+
+def _fuzz_names():
+    from fuzz_configs import FUZZ
+
+    return sorted(FUZZ)
+
+
+@pytest.mark.parametrize("name", _fuzz_names())
+def test_random_configurations(name):
+    """Configurations drawn at random (non-square, wide, narrow, tiny boards; every reward
+    type; beam widths 2..4): the oracle must still equal the reference bit for bit."""
+    assert run_pair(name, range(4), p_invalid=0.1, extra_steps=2) > 0
