@@ -236,6 +236,16 @@ def gpu_arm(args, rank, world, local_rank):
     wall = time.perf_counter() - t_wall0
     launches = env.launch_count - l0
     reps_ms = [e0.elapsed_time(e1)]
+    # C1, the only collective of the design: the per-rollout all-reduce of the episode
+    # statistics (NCCL over NVLink); off the step path, its cost is reported beside it
+    agg, agg_ms = None, None
+    if world > 1:
+        pcbgpu.allreduce_episode_stats(env)  # first call sets up the communicator
+        torch.cuda.synchronize()
+        t_a = time.perf_counter()
+        agg = pcbgpu.allreduce_episode_stats(env)
+        torch.cuda.synchronize()
+        agg_ms = (time.perf_counter() - t_a) * 1e3
     stats = env.episode_stats(reset=True)
     # median of 5 repetitions of the same K-step region (the rollout just goes on)
     for _ in range(REPETITIONS - 1):
@@ -306,7 +316,6 @@ def gpu_arm(args, rank, world, local_rank):
     vals = torch.tensor(reps_ms + [e2e_s * 1e3], dtype=torch.float64, device=env.device)
     if world > 1:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-        agg = pcbgpu.allreduce_episode_stats  # noqa: F841 (C1: the only collective, off the step path)
     *reps_max, e2e_ms_max = vals.tolist()
     ms_max = sorted(reps_max)[len(reps_max) // 2]  # median repetition, each the max over ranks
     total_steps = float(N) * K * world
@@ -373,6 +382,10 @@ def gpu_arm(args, rank, world, local_rank):
                      "mean_length": stats["sum_length"] / max(stats["episodes"], 1)},
         "wall_s_timed_region": wall,
     }
+    if agg is not None:
+        out["episode_stats_allreduce"] = {"ms": agg_ms, "episodes_all_ranks": agg["episodes"],
+                                          "steps_all_ranks": agg["steps"],
+                                          "note": "one NCCL all-reduce of 6 float64 per rollout, outside the timed region"}
     if world == 1 and name == WORKLOAD and not args.no_secondary:
         env.close()
         del env
