@@ -1114,17 +1114,11 @@ step_kernel(const Params p) {
   const int env = blockIdx.x * kWarpsPerCta + wic;
   const bool live = env < p.n_envs;
   // issue every global load of this warp before anything waits: table, state, action
-#if defined(PCB_EXPERIMENT_STORES_ONLY) && PCB_EXPERIMENT_STORES_ONLY == 3
-  const uint4 lut_part = make_uint4(0, 0, 0, 0);
-  const int n16 = sh.st_stride() >> 4;
-  uint4 st0 = make_uint4(1, 2, 3, 4);
-#else
   const uint4 lut_part = expand_lut_fetch();
   const uint8_t* gstate_c = p.state + (size_t)(live ? env : 0) * sh.st_stride();
   const int n16 = sh.st_stride() >> 4;
   uint4 st0 = make_uint4(0, 0, 0, 0);
   if (lane < n16) st0 = reinterpret_cast<const uint4*>(gstate_c)[lane];
-#endif
   const int kind = sh.kind();
   int o = 0, x = 0, y = 0;
   if (live) {  // FlatteningActionWrapper*: env_wrappers.py:80-98, wrapper_square.py:54-69
@@ -1141,35 +1135,6 @@ step_kernel(const Params p) {
   }
   expand_lut_store(smem, lut_part);
   if (!live) return;
-#ifdef PCB_EXPERIMENT_STORES_ONLY
-  {  // measurement only: the store pattern of one step without any of the computation
-#if PCB_EXPERIMENT_STORES_ONLY == 2
-#define PCB_XST(ptr, val) __stcs(ptr, val)
-#else
-#define PCB_XST(ptr, val) (*(ptr) = (val))
-#endif
-    const uint4 zv = make_uint4(lane, o, x, y);
-    uint4* g;
-    g = reinterpret_cast<uint4*>(p.out.grid + (size_t)env * sh.grid_b());
-    for (int i = lane; i < (sh.grid_b() >> 4); i += 32) PCB_XST(g + i, zv);
-    g = reinterpret_cast<uint4*>(p.out.mask + (size_t)env * sh.mask_b());
-    for (int i = lane; i < (sh.mask_b() >> 4); i += 32) PCB_XST(g + i, zv);
-    if (sh.kind() >= 2) {
-      g = reinterpret_cast<uint4*>(p.out.pnum + (size_t)env * sh.pnum_n());
-      for (int i = lane; i < (sh.pnum_n() >> 3); i += 32) PCB_XST(g + i, zv);
-      g = reinterpret_cast<uint4*>(p.out.pcat + (size_t)env * sh.pcat_n());
-      for (int i = lane; i < (sh.pcat_n() >> 3); i += 32) PCB_XST(g + i, zv);
-    }
-    uint32_t* f = reinterpret_cast<uint32_t*>(p.out.feat + (size_t)env * sh.feat_n());
-    for (int i = lane; i < sh.feat_n(); i += 32) f[i] = lane;
-    if (lane < sh.C()) p.out.place_mask[(size_t)env * sh.C() + lane] = 1;
-    g = reinterpret_cast<uint4*>(p.state + (size_t)env * sh.st_stride());
-    if (lane < n16) g[lane] = st0;
-    if (lane == 0) { p.out.done[env] = 0; p.out.reward[env] = 0.0; }
-    if (p.actions_out && lane == 0) { p.actions_out[3 * env] = 0; p.actions_out[3 * env + 1] = 0; p.actions_out[3 * env + 2] = 0; }
-    return;
-  }
-#endif
   Env<T> e(smem + kLutBytes + (size_t)wic * sh.sm_stride(), sh);
   uint8_t* gstate = p.state + (size_t)env * sh.st_stride();
   if (lane < n16) reinterpret_cast<uint4*>(e.sm)[lane] = st0;
