@@ -231,6 +231,13 @@ int pcb_set_reward_overlap(pcb_env_t* env, int on);
 int pcb_set_fused_rollout(pcb_env_t* env, int on);
 int pcb_fused_rollout_times(pcb_env_t* env, double* ms, int64_t* launches, int64_t* steps);
 
+/* Memory-safety aid (compute-sanitizer stand-in): with PCB_GUARD=1 in the environment when
+ * pcb_create runs, every device buffer of the handle is allocated between two 4 KB guard
+ * bands of a known pattern; pcb_check_guards waits for the device and returns the number of
+ * guard bytes that were overwritten (0 = no out-of-bounds store next to any buffer),
+ * negative on error / when the handle has no guards. */
+int64_t pcb_check_guards(pcb_env_t* env, void* stream);
+
 /* Measurement aid: when on, every kernel launch is bracketed by CUDA events on the
  * launching stream.  pcb_kernel_times waits for them and returns the summed device
  * time [ms] and launch count per kernel {step, reward, reset, sample}, then clears. */

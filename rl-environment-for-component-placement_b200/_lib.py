@@ -14,7 +14,7 @@ SYMBOLS = (
     "pcb_last_error", "pcb_abi_version", "pcb_rollout_random", "pcb_enable_kernel_timing",
     "pcb_kernel_times", "pcb_current_result_half", "pcb_generate_host", "pcb_generate_instances_device", "pcb_state_layout", "pcb_get_state",
     "pcb_set_state", "pcb_set_reward_overlap", "pcb_shape_id", "pcb_set_fused_rollout",
-    "pcb_fused_rollout_times", "pcb_rollout_random_logged",
+    "pcb_fused_rollout_times", "pcb_rollout_random_logged", "pcb_check_guards",
 )
 
 
@@ -84,6 +84,8 @@ def load(path=None):
     lib.pcb_launch_count.argtypes = [vp]
     lib.pcb_launch_count.restype = i64
     lib.pcb_rollout_random.argtypes = [vp, u64, i32, vp, vp]
+    lib.pcb_check_guards.argtypes = [vp, vp]
+    lib.pcb_check_guards.restype = i64
     lib.pcb_rollout_random_logged.argtypes = [vp, u64, i32, vp, vp, vp, vp]
     lib.pcb_enable_kernel_timing.argtypes = [vp, i32]
     lib.pcb_set_reward_overlap.argtypes = [vp, i32]

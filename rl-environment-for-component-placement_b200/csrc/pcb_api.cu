@@ -94,6 +94,12 @@ struct pcb_env {
   int64_t fused_launches, fused_steps;
   std::vector<TensorDesc> tensors;
   std::vector<void*> allocs;
+  // PCB_GUARD=1 in the environment at pcb_create: every handle-owned buffer sits between two
+  // guard bands of a known byte pattern that pcb_check_guards verifies (compute-sanitizer is not
+  // available on the test pool; this catches out-of-bounds stores next to any buffer)
+  bool guard;
+  struct Guarded { uint8_t* base; size_t bytes; };
+  std::vector<Guarded> guarded;
   // optional per-kernel CUDA-event timing (pcb_enable_kernel_timing)
   bool timing;
   struct Timed { int id; cudaEvent_t a, b; };
@@ -288,17 +294,26 @@ int small_dispatch(pcb_env* e, bool configure, cudaStream_t st, const RolloutPar
   return small_launch<DynShape, 32>(configure, sm, grid, block, st, p);
 }
 
+constexpr size_t kGuardBytes = 4096;
+constexpr int kGuardByte = 0xA5;
+
 template <typename P>
 int dev_alloc(pcb_env* e, P** out, size_t bytes) {
   void* p = nullptr;
   if (bytes == 0) bytes = 16;
-  cudaError_t err = cudaMalloc(&p, bytes);
+  const size_t pad = e->guard ? kGuardBytes : 0;
+  cudaError_t err = cudaMalloc(&p, bytes + 2 * pad);
   if (err != cudaSuccess)
     return fail(err == cudaErrorMemoryAllocation ? PCB_ERR_NOMEM : PCB_ERR_CUDA,
                 "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(err));
-  CU(cudaMemset(p, 0, bytes));
   e->allocs.push_back(p);
-  *out = reinterpret_cast<P*>(p);
+  uint8_t* base = reinterpret_cast<uint8_t*>(p);
+  if (pad) {
+    CU(cudaMemset(base, kGuardByte, bytes + 2 * pad));
+    e->guarded.push_back({base, bytes});
+  }
+  CU(cudaMemset(base + pad, 0, bytes));
+  *out = reinterpret_cast<P*>(base + pad);
   return 0;
 }
 
@@ -468,6 +483,10 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
   e->device = device; e->n_envs = num_envs; e->ring = cfg->obs_ring; e->slice = 0;
   e->wide = cfg->height > 32 || cfg->width > 32;
   e->step_no = 0; e->launches = 0; e->bank = nullptr; e->bank_count = 0; e->timing = false;
+  {
+    const char* g = getenv("PCB_GUARD");
+    e->guard = g && g[0] == '1';
+  }
   e->ratio_lut = nullptr; e->d_actions = nullptr; e->d_actions2 = nullptr;
   memset(&e->base, 0, sizeof e->base);
   fill_dims(*cfg, false, e->d);
@@ -1016,6 +1035,23 @@ int pcb_set_reward_overlap(pcb_env_t* e, int on) {
   if (!e) return fail(PCB_ERR_INVALID, "env is NULL");
   e->overlap = on != 0;
   return 0;
+}
+
+int64_t pcb_check_guards(pcb_env_t* e, void* stream) {
+  if (!e) return fail(PCB_ERR_INVALID, "env is NULL");
+  if (!e->guard) return fail(PCB_ERR_STATE, "the handle was not created with PCB_GUARD=1");
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize((cudaStream_t)stream));
+  CU(cudaDeviceSynchronize());
+  std::vector<uint8_t> host(kGuardBytes);
+  int64_t bad = 0;
+  for (const pcb_env::Guarded& g : e->guarded)
+    for (int side = 0; side < 2; ++side) {
+      const uint8_t* src = side ? g.base + kGuardBytes + g.bytes : g.base;
+      CU(cudaMemcpy(host.data(), src, kGuardBytes, cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < kGuardBytes; ++i) bad += host[i] != (uint8_t)kGuardByte;
+    }
+  return bad;
 }
 
 int pcb_set_fused_rollout(pcb_env_t* e, int on) {

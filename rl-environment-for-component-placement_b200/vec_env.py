@@ -346,6 +346,11 @@ class PcbVecEnv:
                 "steps")
         return {k: out[i] for i, k in enumerate(keys)}
 
+    def check_guards(self):
+        """Bytes overwritten in the guard bands around the library's device buffers (needs
+        PCB_GUARD=1 in the environment when the env is created); 0 = none."""
+        return int(self._check(self.lib.pcb_check_guards(self._h, self._stream())))
+
     @property
     def shape_id(self):
         """0 = runtime-shaped kernels, 1..99 = built-in compile-time shape, 100 = specialised"""
