@@ -26,7 +26,9 @@ from ref_harness import CONFIGS, make_oracle
 pytestmark = pytest.mark.gpu
 
 FULL = [("A", 65536, 14), ("B", 4096, 20), ("B", 65536, 14), ("C", 65536, 23), ("D", 65536, 13),
-        ("E", 131072, 35)]
+        ("E", 131072, 35),
+        # 2^20 envs on one GPU: 32-bit index arithmetic of the multi-env-per-warp kernel
+        ("A", 1048576, 6), ("B", 1048576, 8)]
 
 
 def window_free(grid, ph, pw):
