@@ -268,6 +268,42 @@ def test_logged_rollout_equals_stepping_by_hand(name):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("name,n", [("C", 20000), ("C_both", 6000), ("D", 6000), ("E", 3000), ("B", 20000)])
+def test_long_rollouts_do_not_depend_on_the_call_pattern(name, n):
+    """600 steps as one call, as many short calls, and with the reward kernels serialised:
+    the overlapped reward pipeline (double-buffered jobs and results, counter ring, two
+    streams) must not change a single byte of state, observations, results or statistics."""
+    T = 600
+    envs = [make(name, n, seed=9, obs_ring=2, bank_size=3 * n) for _ in range(3)]
+    for e in envs:
+        e.reset()
+    envs[0].rollout_random(T, seed=4)
+    done = 0
+    for chunk in [1, 2, 3, 5, 7, 11, 13, 17, 64, 1, 1, 100] * 10:
+        chunk = min(chunk, T - done)
+        if chunk == 0:
+            break
+        envs[1].rollout_random(chunk, seed=4)
+        done += chunk
+    assert done == T
+    envs[2].reward_overlap(False)
+    envs[2].rollout_random(T, seed=4)
+    torch.cuda.synchronize()
+    ref_state, ref_stats = envs[0].state_dict(), envs[0].episode_stats()
+    for e in envs[1:]:
+        sd, st = e.state_dict(), e.episode_stats()
+        assert sd["step_no"] == ref_state["step_no"] and np.array_equal(sd["state"], ref_state["state"])
+        assert st["episodes"] == ref_stats["episodes"] > 0 and st["sum_length"] == ref_stats["sum_length"]
+        for k in ("sum_return", "sum_wirelength", "sum_intersections"):  # atomics: order differs
+            assert np.isclose(st[k], ref_stats[k], rtol=1e-9, atol=0), (name, k)
+        for k in envs[0].obs_ring_tensors:
+            assert torch.equal(e.obs_ring_tensors[k], envs[0].obs_ring_tensors[k]), (name, k)
+        for k in envs[0]._res:
+            assert torch.equal(e._res[k], envs[0]._res[k]), (name, k)
+    for e in envs:
+        e.close()
+
+
 def test_errors_are_loud():
     import pcbgpu
     from pcbgpu._lib import PcbError
