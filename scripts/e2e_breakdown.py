@@ -15,6 +15,8 @@ ge.build()
 import pcbgpu  # noqa: E402
 from ref_harness import CONFIGS  # noqa: E402
 
+if os.environ.get("USE_STREAM"):
+    torch.cuda.set_stream(torch.cuda.Stream())
 NAME = sys.argv[1] if len(sys.argv) > 1 else "C"
 N, K = int(sys.argv[2]) if len(sys.argv) > 2 else 65536, 200
 env = pcbgpu.PcbVecEnv(CONFIGS[NAME], N, autoreset=True, obs_ring=4, bank_size=4 * N, seed=1,
@@ -84,3 +86,5 @@ run("pcb_step, device actions, sync every step", dev_only)
 run("+ H2D of the actions (torch copy)", with_h2d)
 run("+ D2H of reward and done (torch copies)", with_both)
 run("pcb_step_host", step_host)
+stepper = env.host_stepper(h_act, h_r, h_d)
+run("pcb_step_host through host_stepper (pointers bound once)", stepper)

@@ -304,6 +304,26 @@ def test_long_rollouts_do_not_depend_on_the_call_pattern(name, n):
         e.close()
 
 
+def test_host_stepper_equals_step_host():
+    n, T = 200, 9
+    a, b = make("C", n, seed=2), make("C", n, seed=2)
+    a.reset(); b.reset()
+    log = torch.zeros((T, n, 3), dtype=torch.int32, device="cuda")
+    c = make("C", n, seed=2)
+    c.reset(); c.rollout_random(T, seed=1, actions_log=log); c.close()
+    flat = ((log[..., 0] * 32 + log[..., 1]) * 32 + log[..., 2]).int().cpu().pin_memory()
+    ra, da = torch.zeros(n, dtype=torch.float64).pin_memory(), torch.zeros(n, dtype=torch.uint8).pin_memory()
+    rb, db = np.zeros(n, np.float64), np.zeros(n, np.uint8)
+    f = a.host_stepper(flat, ra, da)
+    for t in range(T):
+        f(t)
+        b.step_host(flat[t].numpy(), rb, db)
+        assert np.array_equal(ra.numpy(), rb) and np.array_equal(da.numpy(), db), t
+    with pytest.raises(IndexError):
+        f(T)
+    a.close(); b.close()
+
+
 def test_errors_are_loud():
     import pcbgpu
     from pcbgpu._lib import PcbError
