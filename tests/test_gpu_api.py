@@ -435,3 +435,22 @@ def test_specialised_library_for_an_arbitrary_config():
     run_parity("S_pin", range(32), extra_steps=2, stats=st, specialize=True)
     run_parity("S_pin", range(16), autoreset=True, episodes=2, p_invalid=0.1, stats=st, specialize=True)
     assert st["reward_inexact"] == 0
+
+
+def test_specialised_library_for_a_pin_less_config():
+    """... and for a rectangular configuration: the user shape also instantiates the
+    multi-env-per-warp rollout kernel (12x14 board: 16 lanes per env, dense-bit-string boards)."""
+    import __graft_entry__ as ge
+
+    assert CONFIGS["S_rect"] == ge.SPECIALISED_DEMO_RECT  # the library build() prepared
+    env = make("S_rect", 100, specialize=True, obs_ring=3, seed=1)
+    assert env.shape_id == 100 and env.fused_rollout(True)
+    ref = make("S_rect", 100, obs_ring=3, seed=1)  # runtime-shaped kernels of the default library
+    assert ref.shape_id == 0
+    env.reset(); ref.reset()
+    env.rollout_random(40, seed=3); ref.rollout_random(40, seed=3)
+    for k in env.obs_ring_tensors:
+        assert torch.equal(env.obs_ring_tensors[k], ref.obs_ring_tensors[k]), k
+    assert np.array_equal(env.state_dict()["state"], ref.state_dict()["state"])
+    env.close(); ref.close()
+    run_parity("S_rect", range(24), extra_steps=2, p_invalid=0.2, specialize=True)
