@@ -961,6 +961,7 @@ static int rollout_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_ac
   p.actions_log = d_actions_log;
   p.reward_log = d_reward_log; p.done_log = d_done_log;
   p.seed = seed; p.step_no = e->step_no; p.bank_count = e->bank_count;
+  p.slot_step = e->bank_count ? (uint32_t)e->n_envs % e->bank_count : (uint32_t)e->n_envs;
   p.n_envs = e->n_envs; p.n_steps = n_steps; p.ring = e->ring; p.slice0 = e->slice;
   cudaEvent_t a = nullptr, b = nullptr;
   if (e->timing) {

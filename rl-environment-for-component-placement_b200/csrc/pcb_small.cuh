@@ -1,7 +1,8 @@
 // pcb_small.cuh -- the whole random-policy rollout of the pin-less environments
 // (square: dummy_env_square.py:74-153, rectangle: dummy_env_rectangular.py:310-432) in
 // ONE launch: n_steps x { random policy (agent/random/random_policy_*.py:11-58) -> step ->
-// episode statistics -> auto-reset -> observation write-out }.
+// episode statistics -> auto-reset -> observation write-out }; with the caller's actions
+// instead of the policy the same kernel is pcb_step for these kinds (one step per launch).
 //
 // Why a second kernel: these boards have at most 32 rows and no routing reward, so a step
 // is ~1 KB of output and a few hundred instructions.  One launch per step is launch-bound
@@ -38,6 +39,7 @@ struct RolloutParams {
   uint64_t seed;
   uint64_t step_no;      // number of the first step
   uint32_t bank_count;
+  uint32_t slot_step;    // n_envs % bank_count: the next slot is a conditional subtraction away
   int n_envs, n_steps;
   int ring, slice0;      // step t writes observation slice (slice0 + 1 + t) % ring
 };
@@ -220,8 +222,8 @@ rollout_small_kernel(const __grid_constant__ RolloutParams p) {
   constexpr int kPre = 2;  // components per lane kept in registers: C <= kPre * LPE, else re-read
   uint32_t nxt_hdr = 1u, nxt_comp[kPre] = {0u, 0u};
   auto prefetch = [&](uint32_t cur_slot) {
-    uint32_t s2 = cur_slot + N;
-    if (p.bank_count) s2 %= p.bank_count;
+    uint32_t s2 = cur_slot + p.slot_step;  // (cur_slot + N) % bank_count without a division
+    if (p.bank_count && s2 >= p.bank_count) s2 -= p.bank_count;
     const uint8_t* rec = p.bank + (size_t)s2 * sh.rec_stride();
     nxt_hdr = *reinterpret_cast<const uint32_t*>(rec);
 #pragma unroll
@@ -344,8 +346,8 @@ rollout_small_kernel(const __grid_constant__ RolloutParams p) {
       if (!d.autoreset) flags |= kFlagFinished;
     };
     auto restart = [&]() {  // reset(): next bank slot, empty board (rect:310-351)
-      slot += N;
-      if (p.bank_count) slot %= p.bank_count;
+      slot += p.slot_step;
+      if (p.bank_count && slot >= p.bank_count) slot -= p.bank_count;
       epno += 1;
       if (kind != 0) {
         hdr0 = nxt_hdr; n_comp = nxt_hdr & 0xff;
