@@ -29,6 +29,18 @@ extern "C" {
 
 #define PCB_ABI_VERSION 1
 
+/* Capacities of the library (csrc/pcb_layout.h).  The reference has no such limits; a
+ * configuration or instance outside them is rejected by pcb_create / pcb_upload_instances
+ * with PCB_ERR_INVALID and a message naming the limit -- nothing is truncated silently. */
+#define PCB_MAX_GRID 64            /* height, width: 1..64 (one u32/u64 bitboard word per row) */
+#define PCB_MAX_COMPONENTS 64      /* max_num_components */
+#define PCB_MAX_COMPONENT_SIDE 32  /* max_component_h, max_component_w; h*w <= 255; both must
+                                      fit the grid in either orientation */
+#define PCB_MAX_PINS 512           /* pins per instance */
+#define PCB_MAX_NETS 63            /* max_num_nets */
+#define PCB_MAX_BEAM_WIDTH 4       /* reward_beam_width, reward types beam / both */
+#define PCB_MAX_BEAM_NET_PINS 16   /* pins per net when the beam router runs */
+
 typedef enum {
   PCB_OK = 0,
   PCB_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
@@ -114,7 +126,11 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
 int pcb_destroy(pcb_env_t* env);
 
 /* Replaces the RNG draw of generate_instances (rect:253-273, pin:1006-1035):
- * the instances reset() hands out.  Slot of env i, episode e = (i + e*N) % count. */
+ * the instances reset() hands out.  Slot of env i, episode e = (i + e*N) % count.
+ * The bank may be replaced at any time between calls (this function, pcb_generate_instances,
+ * pcb_generate_instances_device): a running episode is unaffected -- everything it needs
+ * was copied into the per-env state at reset -- and the next episode of an env on slot s
+ * takes slot (s + N) % new_count of the new bank. */
 int pcb_upload_instances(pcb_env_t* env, const pcb_instance_bank_t* host_bank);
 
 /* Fills the bank with `count` instances drawn on the host by the library's own

@@ -10,7 +10,9 @@ environment needs libpcbgpu.so and a CUDA device and fails loudly otherwise.
 from .config import EnvSpec, make_spec, KINDS  # noqa: F401
 from .instances import InstanceBank, generate_bank  # noqa: F401
 from .vec_env import PcbVecEnv  # noqa: F401
-from .gym_compat import GymCompatEnv, create_env, init_env  # noqa: F401
+from .gym_compat import GymCompatEnv, create_env, init_env, init_env_config  # noqa: F401
+from .configs import CONFIGS, SHIPPED_CONFIGS  # noqa: F401
+from . import spaces  # noqa: F401
 from .wrappers import (  # noqa: F401
     FlatteningActionMaskObservationWrapper, FlatteningActionWrapper,
     FlatteningActionMaskObservationWrapperRect, FlatteningActionWrapperRect,

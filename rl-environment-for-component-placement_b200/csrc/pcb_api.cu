@@ -24,6 +24,11 @@
 
 using namespace pcb;
 
+static_assert(PCB_MAX_GRID == kMaxGrid && PCB_MAX_COMPONENTS == kMaxComps && PCB_MAX_PINS == kMaxPins &&
+              PCB_MAX_NETS == kMaxNets - 1 && PCB_MAX_BEAM_WIDTH == kMaxBeamWidth &&
+              PCB_MAX_BEAM_NET_PINS == kMaxBeamPoints + 1,
+              "include/pcb_env.h documents the capacities of csrc/pcb_layout.h");
+
 #ifndef PCB_OVERLAP_REWARD
 #define PCB_OVERLAP_REWARD 1
 #endif
@@ -103,7 +108,9 @@ struct pcb_env {
   // optional per-kernel CUDA-event timing (pcb_enable_kernel_timing)
   bool timing;
   struct Timed { int id; cudaEvent_t a, b; };
-  std::vector<Timed> timed;
+  std::vector<Timed> timed;       // outstanding event pairs, at most kMaxTimed
+  double timed_ms[4];             // totals of the pairs already folded in
+  int64_t timed_n[4];
 };
 
 namespace {
@@ -155,6 +162,23 @@ Params make_params(const pcb_env* e, bool for_reset = false) {
 }
 
 enum KernelId { K_STEP, K_TERM, K_RESET, K_SAMPLE };
+
+// outstanding timing events are bounded: past kMaxTimed pairs the finished ones are folded
+// into running totals (a caller that enables timing and never polls does not grow the list)
+constexpr size_t kMaxTimed = 4096;
+int fold_timed(pcb_env* e) {
+  for (auto& t : e->timed) {
+    CU(cudaEventSynchronize(t.b));
+    float v = 0.f;
+    CU(cudaEventElapsedTime(&v, t.a, t.b));
+    e->timed_ms[t.id] += v;
+    e->timed_n[t.id] += 1;
+    cudaEventDestroy(t.a);
+    cudaEventDestroy(t.b);
+  }
+  e->timed.clear();
+  return 0;
+}
 
 template <typename S>
 bool shape_matches(const Dims& d) {
@@ -255,6 +279,10 @@ int launch(pcb_env* e, KernelId id, const Params& p, cudaStream_t st, int reward
   if (e->timing) {
     CU(cudaEventRecord(tm.b, st));
     e->timed.push_back(tm);
+    if (e->timed.size() >= kMaxTimed) {
+      int rc = fold_timed(e);
+      if (rc) return rc;
+    }
   }
   e->launches += 1;
   return 0;
@@ -483,6 +511,7 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
   e->device = device; e->n_envs = num_envs; e->ring = cfg->obs_ring; e->slice = 0;
   e->wide = cfg->height > 32 || cfg->width > 32;
   e->step_no = 0; e->launches = 0; e->bank = nullptr; e->bank_count = 0; e->timing = false;
+  for (int i = 0; i < 4; ++i) { e->timed_ms[i] = 0.0; e->timed_n[i] = 0; }
   {
     const char* g = getenv("PCB_GUARD");
     e->guard = g && g[0] == '1';
@@ -499,8 +528,9 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
   const Dims& d = e->d;
   e->smem_bytes = (size_t)kLutBytes + (size_t)d.L.sm_stride * kWarpsPerCta;
   if (e->smem_bytes > 200 * 1024) {
+    const size_t need = e->smem_bytes;
     delete e;
-    return fail(PCB_ERR_INVALID, "configuration needs %zu bytes of shared memory per CTA", e->smem_bytes);
+    return fail(PCB_ERR_INVALID, "configuration needs %zu bytes of shared memory per CTA (limit 200 KB)", need);
   }
   auto cleanup = [&](int code) { pcb_destroy(e); return code; };
 #define TRY(x) do { int rc_ = (x); if (rc_) return cleanup(rc_); } while (0)
@@ -636,6 +666,10 @@ int pcb_destroy(pcb_env_t* e) {
     if (e->ev_rew[i]) cudaEventDestroy(e->ev_rew[i]);
   }
   if (e->side) cudaStreamDestroy(e->side);
+  for (auto& t : e->timed) {  // kernel timing enabled but never polled
+    cudaEventDestroy(t.a);
+    cudaEventDestroy(t.b);
+  }
   for (void* p : e->allocs) cudaFree(p);
   if (e->bank) cudaFree(e->bank);
   delete e;
@@ -1077,15 +1111,11 @@ int pcb_enable_kernel_timing(pcb_env_t* e, int on) {
 int pcb_kernel_times(pcb_env_t* e, double ms[4], int64_t launches[4]) {
   if (!e || !ms || !launches) return fail(PCB_ERR_INVALID, "NULL argument");
   CU(cudaSetDevice(e->device));
-  for (int i = 0; i < 4; ++i) { ms[i] = 0.0; launches[i] = 0; }
-  for (auto& t : e->timed) {
-    CU(cudaEventSynchronize(t.b));
-    float v = 0.f;
-    CU(cudaEventElapsedTime(&v, t.a, t.b));
-    ms[t.id] += v;
-    launches[t.id] += 1;
-    cudaEventDestroy(t.a);
-    cudaEventDestroy(t.b);
+  int rc = fold_timed(e);
+  if (rc) return rc;
+  for (int i = 0; i < 4; ++i) {
+    ms[i] = e->timed_ms[i]; launches[i] = e->timed_n[i];
+    e->timed_ms[i] = 0.0; e->timed_n[i] = 0;
   }
   e->timed.clear();
   return 0;

@@ -6,7 +6,8 @@
 // table placement for (int, int) tuples: tuple hash, linear-probe + perturb
 // sequence, growth at 3/5 fill to the next power of two above 4*used, the
 // copy-vs-rebuild choice of set_difference.  The executable specification is
-// oracle/pyset_model.py (checked against real sets in tests/test_pyset_model.py).
+// oracle/pyset_model.py (checked against real CPython sets in
+// tests/test_host.py::test_pyset_model_matches_cpython_sets).
 // One lane routes one net (nets are independent); runs on terminal steps only.
 #ifndef PCB_BEAM_CUH_
 #define PCB_BEAM_CUH_

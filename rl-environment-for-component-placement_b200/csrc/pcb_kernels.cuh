@@ -27,7 +27,7 @@ constexpr unsigned kFull = 0xffffffffu;
 // shapes: every dimension either a compile-time constant or read from Dims
 // ---------------------------------------------------------------------------
 #define PCB_LAYOUT_FIELDS(X)                                                                   \
-  X(O) X(P) X(F) X(st_comps) X(st_pins) X(st_occ) X(st_stride) X(rec_comps) X(rec_pins)        \
+  X(O) X(P) X(F) X(st_comps) X(st_pins) X(st_occ) X(st_orient) X(st_stride) X(rec_comps) X(rec_pins)        \
   X(rec_stride) X(grid_b) X(mask_b) X(feat_n) X(pnum_n) X(pcat_n) X(pgrid_b) X(cgrid_b)        \
   X(sm_mrow) X(sm_stage) X(sm_scr) X(sm_stride) X(pchunk)
 
@@ -444,6 +444,7 @@ struct Env {
   CompRec* comps;
   PinRec* pins;
   T* occ;      // 32*RPL words
+  uint8_t* orient;  // [C] orientation of each placed component (spatial env only)
   T* mrow;     // [2][32*RPL] mask rows of orientation 0 / 1 (generic board path only)
   uint8_t* stage;
   uint8_t* scr;
@@ -455,6 +456,7 @@ struct Env {
         comps(reinterpret_cast<CompRec*>(base + sh.st_comps())),
         pins(reinterpret_cast<PinRec*>(base + sh.st_pins())),
         occ(reinterpret_cast<T*>(base + sh.st_occ())),
+        orient(base + sh.st_orient()),
         mrow(reinterpret_cast<T*>(base + sh.sm_mrow())),
         stage(base + sh.sm_stage()),
         scr(base + sh.sm_scr()) {}
@@ -783,18 +785,24 @@ __device__ __forceinline__ void write_obs(const S& sh, const Params& p, Env<T>& 
     __syncwarp();
   }
 
-  // component_grid (spatial:1677-1697): drawn at reset from the UN-rotated pin
-  // coordinates, i.e. from the bank record, and constant during the episode.
+  // component_grid (spatial:1677-1697): drawn at reset from the UN-rotated pin coordinates
+  // and constant during the episode.  The state holds the pins as rotated by the placements
+  // so far (place_component rotates in place, pin:156-204); orient[c] undoes that, so the
+  // bank record is not read again after reset.
   zero_smem(e.stage, (sh.cgrid_b() + 15) & ~15, lane);
   __syncwarp();
   const int cells = sh.mh() * sh.mw();
   for (int i = lane; i < n_comp * cells; i += 32) e.stage[i * K] = 1;
   __syncwarp();
-  const PinRec* bp = reinterpret_cast<const PinRec*>(
-      p.bank + (size_t)e.hdr->slot * sh.rec_stride() + sh.rec_pins());
   for (int q = lane; q < n_pins; q += 32) {
-    PinRec pr = bp[q];
-    e.stage[((pr.comp * sh.mh() + pr.rx) * sh.mw() + pr.ry) * K + pr.net + 1] = 1;
+    const PinRec pr = e.pins[q];
+    const CompRec r = e.comps[pr.comp];
+    const int oc = e.orient[pr.comp];
+    int rx = pr.rx, ry = pr.ry;
+    if (oc == 1) { rx = r.h - 1 - pr.ry; ry = pr.rx; }
+    else if (oc == 2) { rx = r.h - 1 - pr.rx; ry = r.w - 1 - pr.ry; }
+    else if (oc == 3) { rx = pr.ry; ry = r.w - 1 - pr.rx; }
+    e.stage[((pr.comp * sh.mh() + rx) * sh.mw() + ry) * K + pr.net + 1] = 1;
   }
   __syncwarp();
   copy_out(p.out.cgrid + (size_t)env * sh.cgrid_b(), e.stage, sh.cgrid_b(), lane);
@@ -849,6 +857,8 @@ __device__ __forceinline__ void load_instance(const S& sh, const Params& p, Env<
   }
 #pragma unroll
   for (int k = 0; k < RPL; ++k) e.occ[lane + 32 * k] = T(0);
+  if (sh.kind() == 3)
+    for (int c = lane; c < sh.C(); c += 32) e.orient[c] = 0;
   __syncwarp();
 }
 
@@ -1181,7 +1191,10 @@ step_kernel(const Params p) {
       e.occ[row] = occ[k];
     }
     if (kind != 0) {
-      if (lane == 0) { e.comps[cur].x = (uint8_t)x; e.comps[cur].y = (uint8_t)y; }
+      if (lane == 0) {
+        e.comps[cur].x = (uint8_t)x; e.comps[cur].y = (uint8_t)y;
+        if (kind == 3) e.orient[cur] = (uint8_t)o;
+      }
       if (kind >= 2 && o != 0) {  // Component.place_component (pin:156-204): rotate in place
         const int n_pins = e.hdr->n_pins;
         for (int q = lane; q < n_pins; q += 32) {

@@ -8,6 +8,10 @@
 //            +..  PinRec[max_pins] (comp, rx, ry, net, pin_id u16, flags, rank)
 //            +..  occupancy bitboard: one word per grid row (u32 if the grid fits
 //                 32x32, else u64), 32*RPL words
+//            +..  spatial env only: u8 orient[C], the orientation each component was placed
+//                 with (component_grid is drawn from the UN-rotated pins: the kernel rotates the
+//                 state's pins back instead of re-reading the bank, so a running episode never
+//                 depends on what the bank holds later)
 //   bank   [count][rec_stride]  EnvHdr + CompRec[C] + PinRec[max_pins] as drawn by
 //                 generate_instances (un-rotated pins); reset copies it into state
 //   obs    struct-of-arrays by observation key, [R][N][...], env-major inside a key
@@ -80,7 +84,7 @@ struct __align__(8) PinRec {
 // very same numbers.
 struct Layout {
   int O, P, F;
-  int st_comps, st_pins, st_occ, st_stride;
+  int st_comps, st_pins, st_occ, st_orient, st_stride;
   int rec_comps, rec_pins, rec_stride;
   int grid_b, mask_b, feat_n, pnum_n, pcat_n, pgrid_b, cgrid_b;
   int sm_mrow, sm_stage, sm_scr, sm_stride;
@@ -117,7 +121,8 @@ PCB_HD constexpr Layout make_layout(int kind, int H, int W, int C, int mh, int m
   L.st_comps = 32;
   L.st_pins = L.st_comps + align16c(C * 4);
   L.st_occ = L.st_pins + align16c(max_pins * 8);
-  L.st_stride = align16c(L.st_occ + rows * word);
+  L.st_orient = L.st_occ + rows * word;
+  L.st_stride = align16c(L.st_orient + (kind == 3 ? align16c(C) : 0));
   L.rec_comps = 16;
   L.rec_pins = L.rec_comps + align16c(C * 4);
   L.rec_stride = L.rec_pins + align16c(max_pins * 8);

@@ -211,6 +211,10 @@ rollout_small_kernel(const __grid_constant__ RolloutParams p) {
     const uint4 d4 = *reinterpret_cast<const uint4*>(gs + 16);
     hdr0 = h4.x; n_comp = h4.x & 0xff; cur = h4.y & 0xff; flags = (h4.y >> 8) & 0xff;
     slot = h4.z; ep_len = h4.w;
+    // the bank may have been replaced by a smaller one since this episode started
+    // (pcb_upload_instances / pcb_generate_instances*): the +slot_step / subtract-once
+    // update below needs slot < bank_count
+    if (p.bank_count && slot >= p.bank_count) slot %= p.bank_count;
     ep_ret = __longlong_as_double((long long)(((uint64_t)d4.y << 32) | d4.x));
     epno = ((uint64_t)d4.w << 32) | d4.z;
   }

@@ -14,6 +14,7 @@ from types import SimpleNamespace
 import numpy as np
 import torch
 
+from . import spaces as _spaces
 from .vec_env import OBS_KEYS, PcbVecEnv
 from .wrappers import (FlatteningActionMaskObservationWrapperRect,
                        FlatteningActionMaskObservationWrapperSquare,
@@ -29,6 +30,9 @@ class GymCompatEnv:
         self.height, self.width = self.spec.height, self.spec.width
         self.action_sizes = ([self.height, self.width] if self.kind == "square"
                              else [self.spec.n_orient, self.height, self.width])
+        # the reference's gym spaces (square:53-65, rect:193-230, pin:482-542, spatial:487-551)
+        self.action_space = _spaces.action_space(self.spec)
+        self.observation_space = _spaces.observation_space(self.spec)
         self.max_wirelength = self.spec.max_wirelength
         self.max_num_intersections = self.spec.max_num_intersections
         self.reward_wirelength, self.reward_intersection = -1.0, -1
@@ -117,9 +121,29 @@ class GymCompatEnv:
         self._vec.close()
 
 
-def init_env(env_config, **kw):
-    """utils/agent/utils.py:317-391."""
-    return GymCompatEnv(env_config, **kw)
+_PIN_TYPES = ("rectangle_pin", "rectangle_factorized_pin", "rectangle_pin_attn_component",
+              "rectangle_pin_attn_all", "rectangle_pin_attn_all_no_grid",
+              "rectangle_pin_all_attn_factorized", "rectangle_spatial_pin")
+
+
+def init_env(env_config, forward_weight_num_intersections=False, **kw):
+    """utils/agent/utils.py:317-391.
+
+    The reference's ``init_env`` passes 17 of the 18 constructor arguments of the pin
+    environments: ``env_config["weight_num_intersections"]`` is never forwarded (:352-390), so
+    its environments always run with the constructor default 0.5 whatever the JSON says.
+    The default here does the same, so that ``create_env`` returns the reference's rewards on
+    the reference's own config files; ``forward_weight_num_intersections=True`` honours the key.
+    """
+    return GymCompatEnv(init_env_config(env_config, forward_weight_num_intersections), **kw)
+
+
+def init_env_config(env_config, forward_weight_num_intersections=False):
+    """The constructor arguments the reference's ``init_env`` really uses, as an env_config."""
+    cfg = dict(env_config)
+    if cfg.get("type") in _PIN_TYPES and not forward_weight_num_intersections:
+        cfg["weight_num_intersections"] = 0.5  # pin:415 / spatial:415 constructor default
+    return cfg
 
 
 def create_env(env_config, **kw):

@@ -29,12 +29,31 @@ RESULT_KEYS = ("reward", "done", "wirelength", "num_intersections", "episode_ret
                "episode_length")
 
 
+def _host_buffer(x, dtype, what):
+    """Address of a host buffer handed to the C ABI as a raw pointer: the dtype, device and
+    layout are checked here because the library cannot (a float32 reward buffer or a strided
+    action array would be silently misread or overrun)."""
+    if isinstance(x, torch.Tensor):
+        if x.is_cuda:
+            raise ValueError(f"{what} must be a host (CPU) buffer")
+        ok, have = x.dtype == getattr(torch, dtype) and x.is_contiguous(), x.dtype
+        addr = x.data_ptr()
+    else:
+        x = np.asarray(x) if not isinstance(x, np.ndarray) else x
+        ok = x.dtype == np.dtype(dtype) and x.flags["C_CONTIGUOUS"] and (
+            what == "actions" or x.flags["WRITEABLE"])
+        have, addr = x.dtype, x.__array_interface__["data"][0]
+    if not ok:
+        raise ValueError(f"{what} must be a C-contiguous {dtype} buffer, got {have}")
+    return addr
+
+
 class HostStepper:
     """See PcbVecEnv.host_stepper."""
 
     def __init__(self, env, actions, reward, done):
-        def addr(x):
-            return x.data_ptr() if isinstance(x, torch.Tensor) else x.__array_interface__["data"][0]
+        def addr(x, dtype, what):
+            return _host_buffer(x, dtype, what)
 
         n = env.num_envs
         if tuple(actions.shape[1:]) not in ((n,), (n, env.spec.action_width)):
@@ -45,7 +64,8 @@ class HostStepper:
         self._env, self._fn, self._h = env, env.lib.pcb_step_host, env._h
         self._fmt = 1 if len(actions.shape) == 2 else 0
         row = n * (1 if self._fmt else env.spec.action_width) * 4
-        self._a0, self._row, self._r, self._d = addr(actions), row, addr(reward), addr(done)
+        self._a0, self._row = addr(actions, "int32", "actions"), row
+        self._r, self._d = addr(reward, "float64", "reward"), addr(done, "uint8", "done")
         self._steps = int(actions.shape[0])
         self._stream = torch.cuda.current_stream(env.device).cuda_stream
 
@@ -290,10 +310,14 @@ class PcbVecEnv:
         actions_np int32 [N] (flat) or [N, k]; reward_np float64 [N]; done_np uint8 [N];
         C-contiguous, ideally pinned."""
         fmt = 1 if actions_np.ndim == 1 else 0
-        # (ndarray.ctypes builds a helper object per access, ~2 us each: use the array interface)
-        a = actions_np.__array_interface__["data"][0]
-        r = reward_np.__array_interface__["data"][0]
-        d = done_np.__array_interface__["data"][0]
+        n = self.num_envs
+        if tuple(actions_np.shape) not in ((n,), (n, self.spec.action_width)):
+            raise ValueError(f"actions must have shape [{n}] or [{n}, {self.spec.action_width}]")
+        if tuple(reward_np.shape) != (n,) or tuple(done_np.shape) != (n,):
+            raise ValueError("reward and done must have shape [num_envs]")
+        a = _host_buffer(actions_np, "int32", "actions")
+        r = _host_buffer(reward_np, "float64", "reward")
+        d = _host_buffer(done_np, "uint8", "done")
         self._check(self.lib.pcb_step_host(self._h, a, fmt, r, d, self._stream()))
 
     def host_stepper(self, actions, reward, done):

@@ -9,10 +9,14 @@ and flat actions (decoded inside the step kernel) instead.
 """
 import numpy as np
 
+from . import spaces as _spaces
+
 
 class _Wrapper:
     def __init__(self, env):
         self.env = env
+        self.action_space = getattr(env, "action_space", None)
+        self.observation_space = getattr(env, "observation_space", None)
 
     def __getattr__(self, name):
         if name.startswith("_") or name == "env":
@@ -28,6 +32,11 @@ class _Wrapper:
 
 class FlatteningActionMaskObservationWrapperRect(_Wrapper):
     """env_wrappers.py:9-51 (Rect) / 113-155 (Square) / wrapper_square.py:9-28."""
+
+    def __init__(self, env):
+        super().__init__(env)
+        if self.observation_space is not None:  # env_wrappers.py:28-33
+            self.observation_space = _spaces.flattened_mask_observation_space(self.observation_space)
 
     def observation(self, observation):
         return {k: (np.asarray(v).ravel() if k == "action_mask" else v)
@@ -46,7 +55,12 @@ class FlatteningActionWrapperRect(_Wrapper):
 
     def __init__(self, env):
         super().__init__(env)
-        self.factor_sizes = list(env.action_sizes)
+        if self.action_space is not None:  # env_wrappers.py:74-78
+            assert hasattr(self.action_space, "spaces"), "the action space must be a Tuple"
+            self.factor_sizes = [int(s.n) for s in self.action_space.spaces]
+            self.action_space = _spaces.flat_action_space(self.action_space)
+        else:
+            self.factor_sizes = list(env.action_sizes)
         self.n = int(np.prod(self.factor_sizes))
 
     def action(self, action):

@@ -15,22 +15,12 @@ import numpy as np
 REF_ROOT = os.environ.get("PCB_REF", "/root/reference")
 _STUB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "refstub")
 
-CONFIGS = {
-    # canonical configs of SURVEY.md section 8 / BASELINE.md section 2
-    "A": dict(type="square", height=8, width=8, component_n=3),
-    "A2": dict(type="square", height=8, width=8, component_n=2),
-    "B": dict(type="rectangle", height=16, width=16, min_component_w=2, max_component_w=4,
-              min_component_h=2, max_component_h=4, max_num_components=6, min_num_components=6),
-    "C": dict(type="rectangle_pin", height=32, width=32, net_distribution=9, pin_spread=9,
-              min_component_w=2, max_component_w=4, min_component_h=2, max_component_h=4,
-              max_num_components=10, min_num_components=10, min_num_nets=5, max_num_nets=5,
-              max_num_pins_per_net=6, min_num_pins_per_net=2, reward_type="centroid",
-              reward_beam_width=2, weight_wirelength=0.5, weight_num_intersections=0.5),
-    "E": dict(type="rectangle_pin", height=64, width=64, net_distribution=9, pin_spread=9,
-              min_component_w=2, max_component_w=4, min_component_h=2, max_component_h=4,
-              max_num_components=32, min_num_components=32, min_num_nets=16, max_num_nets=16,
-              max_num_pins_per_net=6, min_num_pins_per_net=2, reward_type="centroid",
-              reward_beam_width=2, weight_wirelength=0.5, weight_num_intersections=0.5),
+from pcbgpu.configs import CONFIGS as _CANONICAL, SHIPPED_CONFIGS  # noqa: E402,F401
+
+# canonical configs A-E, C_both/C_beam, D, D_both, REF_*: pcbgpu/configs.py (the package owns them;
+# bench.py and examples/ read them from there too)
+CONFIGS = {k: dict(v) for k, v in _CANONICAL.items()}
+CONFIGS.update({
     # small / ragged configs for differential testing
     "S_sq": dict(type="square", height=11, width=10, component_n=3),
     "S_rect": dict(type="rectangle", height=12, width=14, min_component_w=1, max_component_w=5,
@@ -56,7 +46,7 @@ CONFIGS = {
                         min_num_nets=2, max_num_nets=3, max_num_pins_per_net=5,
                         min_num_pins_per_net=2, reward_type="centroid", reward_beam_width=2,
                         weight_wirelength=0.5, weight_num_intersections=0.5),
-}
+})
 CONFIGS["S_wide_pin"] = dict(  # 64-bit rows, runtime-shaped kernels, non-square grid
     type="rectangle_pin", height=40, width=50, net_distribution=3, pin_spread=6,
     min_component_w=2, max_component_w=6, min_component_h=1, max_component_h=5,
@@ -69,18 +59,8 @@ CONFIGS["S_wide_sq"] = dict(type="square", height=64, width=64, component_n=5)
 CONFIGS["S_wide_rect"] = dict(type="rectangle", height=33, width=64, min_component_w=3,
                               max_component_w=9, min_component_h=2, max_component_h=8,
                               max_num_components=14, min_num_components=8)
-CONFIGS["C_both"] = dict(CONFIGS["C"], reward_type="both")
-CONFIGS["C_beam"] = dict(CONFIGS["C"], reward_type="beam")
-CONFIGS["D"] = dict(CONFIGS["C"], type="rectangle_spatial_pin")
-CONFIGS["D_both"] = dict(CONFIGS["C"], type="rectangle_spatial_pin", reward_type="both")
 CONFIGS["S_spa"] = dict(CONFIGS["S_pin"], type="rectangle_spatial_pin")
 CONFIGS["S_spa_tight"] = dict(CONFIGS["S_pin_tight"], type="rectangle_spatial_pin")
-CONFIGS["REF_pin"] = dict(  # agent/config/rectangle_pin_model.json
-    type="rectangle_pin", height=10, width=10, net_distribution=9, pin_spread=9,
-    min_component_w=2, max_component_w=2, min_component_h=2, max_component_h=2,
-    max_num_components=5, min_num_components=5, min_num_nets=3, max_num_nets=3,
-    max_num_pins_per_net=6, min_num_pins_per_net=6, reward_type="centroid",
-    reward_beam_width=2, weight_wirelength=0.5, weight_num_intersections=0.5)
 
 
 def reference_available():
@@ -180,11 +160,6 @@ def pick_action(rng, mask, p_invalid=0.0):
     return tuple(int(v) for v in valid[rng.integers(0, len(valid))])
 
 # the reference's other shipped configurations (agent/config/*.json), all 10x10
-CONFIGS["REF_spatial"] = dict(CONFIGS["REF_pin"], type="rectangle_spatial_pin")
-CONFIGS["REF_rect"] = dict(type="rectangle", height=10, width=10, min_component_w=2,
-                           min_component_h=2, max_component_w=4, max_component_h=4,
-                           max_num_components=20, min_num_components=20)
-CONFIGS["REF_square"] = dict(type="square", height=10, width=10, component_n=2)
 # many small components on a small board: more component rows than lanes per env in the
 # multi-env-per-warp rollout kernel (8 lanes per env, 20 rows)
 CONFIGS["S_rect_many"] = dict(type="rectangle", height=8, width=8, min_component_w=1,

@@ -225,3 +225,27 @@ def test_library_generator_matches_reference_distribution(pcbgpu):
         for k in lib_stats:
             p = stats.ks_2samp(lib_stats[k], ref_stats[k]).pvalue
             assert p > 1e-3, (name, k, p, np.mean(lib_stats[k]), np.mean(ref_stats[k]))
+
+
+def test_host_buffers_are_validated_before_their_address_is_taken():
+    """pcb_step_host gets raw pointers: wrong dtype / layout must raise, not be misread"""
+    import numpy as np
+    import pytest
+    import torch
+
+    from pcbgpu.vec_env import _host_buffer
+
+    assert _host_buffer(np.zeros(4, np.int32), "int32", "actions")
+    assert _host_buffer(torch.zeros(4, dtype=torch.float64), "float64", "reward")
+    with pytest.raises(ValueError):
+        _host_buffer(np.zeros(4, np.int64), "int32", "actions")
+    with pytest.raises(ValueError):
+        _host_buffer(np.zeros((4, 6), np.int32)[:, ::2], "int32", "actions")
+    with pytest.raises(ValueError):
+        _host_buffer(np.zeros(4, np.float32), "float64", "reward")
+    with pytest.raises(ValueError):
+        _host_buffer(torch.zeros(4, dtype=torch.int32), "uint8", "done")
+    ro = np.zeros(4, np.uint8)
+    ro.flags.writeable = False
+    with pytest.raises(ValueError):
+        _host_buffer(ro, "uint8", "done")
