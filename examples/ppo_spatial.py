@@ -7,13 +7,12 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 
 import __graft_entry__ as ge  # noqa: E402
 
 pcbgpu = ge.build()
 from pcbgpu.ppo import PPOTrainer  # noqa: E402
-from ref_harness import CONFIGS  # noqa: E402
+from pcbgpu.configs import CONFIGS  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--envs", type=int, default=4096)

@@ -175,10 +175,22 @@ int pcb_step(pcb_env_t* env, const int32_t* d_actions, int action_format, void* 
 int pcb_sample_random_actions(pcb_env_t* env, uint64_t seed, int32_t* d_actions, void* stream);
 
 /* step() through HOST buffers: copies h_actions (ideally pinned) to the device,
- * steps, copies reward[N] (f64) and done[N] (u8) back and waits for them.
- * This is the call the end-to-end benchmark times. */
+ * steps, copies reward[N] (f64) and done[N] (u8) back and waits for them.  When the two
+ * result buffers are one packed block -- h_done == (uint8_t*)(h_reward + N) -- both come
+ * back in ONE device-to-host copy (the library keeps them side by side on the device). */
 int pcb_step_host(pcb_env_t* env, const int32_t* h_actions, int action_format,
                   double* h_reward, uint8_t* h_done, void* stream);
+
+/* n_steps calls of step() for a caller that already holds the action rows (replay of a
+ * recorded rollout, evaluation of a fixed plan, a policy that emits several rows at once):
+ * h_actions [n_steps, N] flat or [n_steps, N, 2|3] tuples; h_reward [n_steps, N] f64 and
+ * h_done [n_steps, N] u8 receive every step's results.  Every step still pays its own
+ * host-to-device copy of its action row and device-to-host copy of its result rows, but
+ * the copies ride on the copy engines while the kernels of neighbouring steps run, and the
+ * host waits once, at the end (the pin-less kinds run all rows in one launch of the
+ * multi-step kernel).  Bit-identical to n_steps x pcb_step_host.  Synchronises `stream`. */
+int pcb_steps_host(pcb_env_t* env, const int32_t* h_actions, int n_steps, int action_format,
+                   double* h_reward, uint8_t* h_done, void* stream);
 
 /* Observation / result tensors as non-owning DLPack views, valid until
  * pcb_destroy.  Keys: the reference's observation keys (grid, action_mask,
@@ -230,6 +242,14 @@ int pcb_rollout_random(pcb_env_t* env, uint64_t seed, int n_steps, int32_t* d_ac
  * produced without a host round trip per step. */
 int pcb_rollout_random_logged(pcb_env_t* env, uint64_t seed, int n_steps, int32_t* d_actions_log,
                               double* d_reward_log, uint8_t* d_done_log, void* stream);
+
+/* The per-step kinds (pin, pin-spatial, boards wider than 32) run pcb_rollout_random as
+ * replays of a CUDA graph of L steps (L = a multiple of the observation ring and of 4, about
+ * 16 steps: step kernels, overlapped reward kernels and their events captured once), the
+ * remainder with plain launches -- default on; results are identical either way.  Small
+ * batches are launch-bound without it.  pcb_graph_replays: graph launches so far. */
+int pcb_set_graph_rollout(pcb_env_t* env, int on);
+int64_t pcb_graph_replays(pcb_env_t* env);
 
 /* pcb_rollout_random runs the reward kernel of step t concurrently with the step kernel of
  * step t+1 (default on); 0 = strictly one after the other, as pcb_step always does. */

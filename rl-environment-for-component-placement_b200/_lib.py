@@ -14,7 +14,8 @@ SYMBOLS = (
     "pcb_last_error", "pcb_abi_version", "pcb_rollout_random", "pcb_enable_kernel_timing",
     "pcb_kernel_times", "pcb_current_result_half", "pcb_generate_host", "pcb_generate_instances_device", "pcb_state_layout", "pcb_get_state",
     "pcb_set_state", "pcb_set_reward_overlap", "pcb_shape_id", "pcb_set_fused_rollout",
-    "pcb_fused_rollout_times", "pcb_rollout_random_logged", "pcb_check_guards",
+    "pcb_fused_rollout_times", "pcb_rollout_random_logged", "pcb_check_guards", "pcb_steps_host",
+    "pcb_set_graph_rollout", "pcb_graph_replays",
 )
 
 
@@ -72,6 +73,7 @@ def load(path=None):
     lib.pcb_step.argtypes = [vp, vp, i32, vp]
     lib.pcb_sample_random_actions.argtypes = [vp, u64, vp, vp]
     lib.pcb_step_host.argtypes = [vp, vp, i32, vp, vp, vp]
+    lib.pcb_steps_host.argtypes = [vp, vp, i32, i32, vp, vp, vp]
     lib.pcb_get_tensor.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
     lib.pcb_current_slice.argtypes = [vp]
     lib.pcb_current_result_half.argtypes = [vp]
@@ -90,6 +92,9 @@ def load(path=None):
     lib.pcb_enable_kernel_timing.argtypes = [vp, i32]
     lib.pcb_set_reward_overlap.argtypes = [vp, i32]
     lib.pcb_set_fused_rollout.argtypes = [vp, i32]
+    lib.pcb_set_graph_rollout.argtypes = [vp, i32]
+    lib.pcb_graph_replays.argtypes = [vp]
+    lib.pcb_graph_replays.restype = i64
     lib.pcb_fused_rollout_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64),
                                             ctypes.POINTER(i64)]
     lib.pcb_kernel_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]

@@ -29,6 +29,9 @@ static_assert(PCB_MAX_GRID == kMaxGrid && PCB_MAX_COMPONENTS == kMaxComps && PCB
               PCB_MAX_BEAM_NET_PINS == kMaxBeamPoints + 1,
               "include/pcb_env.h documents the capacities of csrc/pcb_layout.h");
 
+#ifndef PCB_PERSIST_CTAS
+#define PCB_PERSIST_CTAS PCB_MIN_BLOCKS
+#endif
 #ifndef PCB_OVERLAP_REWARD
 #define PCB_OVERLAP_REWARD 1
 #endif
@@ -61,6 +64,7 @@ struct TensorDesc {
   int code, bits;
   std::vector<int64_t> shape;  // full shape, [R, N, ...] or [N]
   bool ringed;
+  std::vector<int64_t> strides;  // in elements; empty = contiguous
 };
 
 }  // namespace
@@ -81,6 +85,26 @@ struct pcb_env {
   double* stats;
   int32_t* d_actions;  // staging for pcb_step_host / ping-pong of pcb_rollout_random
   int32_t* d_actions2;
+  // reward and done of one step sit side by side ([reward f64 x N | done u8 x N], one block
+  // per result half) so that pcb_step_host brings both back with ONE device-to-host copy
+  size_t res_stride;   // bytes between the two halves
+  // pcb_steps_host: device staging of T action rows and T result rows, a copy stream so that
+  // the upload of later rows overlaps the first steps, events per chunk of rows
+  int32_t* hs_actions; double* hs_reward; uint8_t* hs_done;
+  size_t hs_steps;     // capacity in steps
+  cudaStream_t copy;
+  std::vector<cudaEvent_t> hs_events;
+  cudaEvent_t ev_host;
+  // pcb_rollout_random of the per-step kinds as a CUDA graph of `graph_len` steps (the step
+  // kernels, the overlapped reward kernels on the side stream and their events captured once)
+  bool use_graph;
+  cudaGraphExec_t graph;
+  int graph_len, graph_slice;
+  uint64_t graph_next_step, graph_seed;  // replay is valid when the handle is exactly here
+  cudaStream_t graph_stream;
+  bool graph_overlap;
+  uint64_t* d_step_base;
+  int64_t graph_launches, graph_replays;
   float* ratio_lut;
   int shape_id;        // 0 = generic (DynShape), 1..4 = ShapeB/C/D/E
   uint8_t* jobs;       // routing jobs (pin kinds)
@@ -127,7 +151,9 @@ Out slice_ptrs(const pcb_env* e, int slice, int parity) {
   const Dims& d = e->d;
   const size_t N = (size_t)e->n_envs, s = (size_t)slice, q = (size_t)parity;
   Out o = e->base;
-  o.reward += q * N; o.done += q * N; o.wl += q * N; o.ni += q * N;
+  o.reward = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(o.reward) + q * e->res_stride);
+  o.done += q * e->res_stride;
+  o.wl += q * N; o.ni += q * N;
   o.ep_return += q * N; o.ep_length += q * N;
   if (o.grid) o.grid += s * N * d.L.grid_b;
   if (o.mask) o.mask += s * N * d.L.mask_b;
@@ -237,6 +263,10 @@ int set_smem_shape(size_t bytes) {
 
 int launch(pcb_env* e, KernelId id, const Params& p, cudaStream_t st, int reward_grid = 0) {
   dim3 grid((e->n_envs + kWarpsPerCta - 1) / kWarpsPerCta), block(kWarpsPerCta * 32);
+#if PCB_OPT_PERSIST
+  // persistent step kernel: as many CTAs as are resident at once (PCB_PERSIST_CTAS per SM)
+  if (id == K_STEP) grid.x = std::min<unsigned>(grid.x, (unsigned)(e->sms * PCB_PERSIST_CTAS));
+#endif
   size_t sm = id == K_SAMPLE ? 0 : e->smem_bytes;
   pcb_env::Timed tm{(int)id, nullptr, nullptr};
   if (e->timing) {
@@ -296,8 +326,35 @@ int small_launch(bool configure, size_t sm, dim3 grid, dim3 block, cudaStream_t 
   return 0;
 }
 
+// Lanes per env = the smallest power of two >= H: the most envs per warp.  Spreading a small
+// batch over more warps (wider groups, idle lanes) was measured and is slower: B at 4 096 envs
+// 3.1e9 env-steps/s with 16 lanes per env, 1.9e9 with 32 (PCB_SMALL_LPE forces a width).
+int small_pick_lpe(const pcb_env* e) {
+  const int lpe = small_lanes_per_env(e->d.H);
+  if (const char* f = getenv("PCB_SMALL_LPE")) {
+    const int v = atoi(f);
+    if ((v == 8 || v == 16 || v == 32) && v >= lpe) return v;
+  }
+  return lpe;
+}
+
+template <typename S>
+int small_launch_lpe(int lpe, bool configure, size_t sm, dim3 grid, dim3 block, cudaStream_t st,
+                     const RolloutParams& p) {
+  constexpr int kMin = S::fixed ? small_lanes_per_env(S::kH) : 8;
+  if (configure) {  // every instantiation the dispatcher may pick later
+    int rc = 0;
+    if constexpr (kMin <= 8) rc = rc ? rc : small_launch<S, 8>(true, sm, grid, block, st, p);
+    if constexpr (kMin <= 16) rc = rc ? rc : small_launch<S, 16>(true, sm, grid, block, st, p);
+    return rc ? rc : small_launch<S, 32>(true, sm, grid, block, st, p);
+  }
+  if constexpr (kMin <= 8) if (lpe == 8) return small_launch<S, 8>(false, sm, grid, block, st, p);
+  if constexpr (kMin <= 16) if (lpe == 16) return small_launch<S, 16>(false, sm, grid, block, st, p);
+  return small_launch<S, 32>(false, sm, grid, block, st, p);
+}
+
 int small_dispatch(pcb_env* e, bool configure, cudaStream_t st, const RolloutParams& p) {
-  const int lpe = small_lanes_per_env(e->d.H), G = 32 / lpe;
+  const int lpe = configure ? small_lanes_per_env(e->d.H) : small_pick_lpe(e), G = 32 / lpe;
   // few envs: one-warp CTAs spread evenly over the SMs (all resident at once); many: 4 warps
   const int warps = (e->n_envs + G - 1) / G;
   const int wpc = warps <= e->sms * 32 ? 1 : kWarpsPerCta;
@@ -305,21 +362,19 @@ int small_dispatch(pcb_env* e, bool configure, cudaStream_t st, const RolloutPar
   const size_t sm = configure ? e->small_smem
                               : (size_t)kLutBytes + (size_t)small_env_smem(e->d.C, e->d.H * e->d.W) * wpc * G;
   switch (e->shape_id) {
-    case 1: return small_launch<ShapeB, 16>(configure, sm, grid, block, st, p);
-    case 7: return small_launch<ShapeRefRect, 16>(configure, sm, grid, block, st, p);
-    case 8: return small_launch<ShapeRefSquare, 16>(configure, sm, grid, block, st, p);
-    case 9: return small_launch<ShapeA, 8>(configure, sm, grid, block, st, p);
+    case 1: return small_launch_lpe<ShapeB>(lpe, configure, sm, grid, block, st, p);
+    case 7: return small_launch_lpe<ShapeRefRect>(lpe, configure, sm, grid, block, st, p);
+    case 8: return small_launch_lpe<ShapeRefSquare>(lpe, configure, sm, grid, block, st, p);
+    case 9: return small_launch_lpe<ShapeA>(lpe, configure, sm, grid, block, st, p);
 #ifdef PCB_USER_SHAPE
     case 100:
       if constexpr (kUserDims[0] <= 1 && !kUserWide)
-        return small_launch<ShapeUser, small_lanes_per_env(kUserDims[1])>(configure, sm, grid, block, st, p);
+        return small_launch_lpe<ShapeUser>(lpe, configure, sm, grid, block, st, p);
       break;
 #endif
     default: break;
   }
-  if (lpe == 8) return small_launch<DynShape, 8>(configure, sm, grid, block, st, p);
-  if (lpe == 16) return small_launch<DynShape, 16>(configure, sm, grid, block, st, p);
-  return small_launch<DynShape, 32>(configure, sm, grid, block, st, p);
+  return small_launch_lpe<DynShape>(lpe, configure, sm, grid, block, st, p);
 }
 
 constexpr size_t kGuardBytes = 4096;
@@ -477,6 +532,7 @@ int pack_and_upload(pcb_env* e, const pcb_instance_bank_t* b) {
       }
     }
   }
+  if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }  // it carries the old bank pointer
   if (e->bank) { cudaFree(e->bank); e->bank = nullptr; }
   void* p = nullptr;
   CU(cudaMalloc(&p, host.size()));
@@ -517,6 +573,11 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
     e->guard = g && g[0] == '1';
   }
   e->ratio_lut = nullptr; e->d_actions = nullptr; e->d_actions2 = nullptr;
+  e->res_stride = 0; e->hs_actions = nullptr; e->hs_reward = nullptr; e->hs_done = nullptr;
+  e->hs_steps = 0; e->copy = nullptr; e->ev_host = nullptr;
+  e->use_graph = true; e->graph = nullptr; e->graph_len = 0; e->graph_slice = 0; e->graph_next_step = 0;
+  e->graph_seed = 0; e->graph_stream = nullptr; e->graph_overlap = false; e->d_step_base = nullptr;
+  e->graph_launches = 0; e->graph_replays = 0;
   memset(&e->base, 0, sizeof e->base);
   fill_dims(*cfg, false, e->d);
   e->shape_id = cfg->reserved0 == 1 ? 0 : pick_shape(e->d);  // reserved0 == 1 forces the generic kernels (tests)
@@ -595,6 +656,7 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
   TRY(dev_alloc(e, &e->stats, kStatSlots * 8 * sizeof(double)));
   TRY(dev_alloc(e, &e->d_actions, N * 3 * sizeof(int32_t)));
   TRY(dev_alloc(e, &e->d_actions2, N * 3 * sizeof(int32_t)));
+  TRY(dev_alloc(e, &e->d_step_base, sizeof(uint64_t)));
   if (d.kind >= 2) {
     TRY(dev_alloc(e, &e->jobs, 2 * N * (size_t)job_stride(d.max_pins, d.K)));
     TRY(dev_alloc(e, &e->job_count, 4 * sizeof(uint32_t)));
@@ -641,10 +703,17 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
       add("component_grid", (void**)&e->base.cgrid, kDLUInt, 8, {r64, n64, d.C, d.mh, d.mw, d.K}, true);
     }
   }
-  TRY(dev_alloc(e, &e->base.reward, 2 * N * sizeof(double)));
-  add("reward", (void**)&e->base.reward, kDLFloat, 64, {2, n64}, false);
-  TRY(dev_alloc(e, &e->base.done, 2 * N));
-  add("done", (void**)&e->base.done, kDLUInt, 8, {2, n64}, false);
+  {
+    e->res_stride = (N * 9 + 15) & ~(size_t)15;
+    uint8_t* blk = nullptr;
+    TRY(dev_alloc(e, &blk, 2 * e->res_stride));
+    e->base.reward = reinterpret_cast<double*>(blk);
+    e->base.done = blk + N * sizeof(double);
+    add("reward", (void**)&e->base.reward, kDLFloat, 64, {2, n64}, false);
+    e->tensors.back().strides = {(int64_t)(e->res_stride / sizeof(double)), 1};
+    add("done", (void**)&e->base.done, kDLUInt, 8, {2, n64}, false);
+    e->tensors.back().strides = {(int64_t)e->res_stride, 1};
+  }
   TRY(dev_alloc(e, &e->base.wl, 2 * N * sizeof(double)));
   add("wirelength", (void**)&e->base.wl, kDLFloat, 64, {2, n64}, false);
   TRY(dev_alloc(e, &e->base.ni, 2 * N * sizeof(double)));
@@ -666,6 +735,13 @@ int pcb_destroy(pcb_env_t* e) {
     if (e->ev_rew[i]) cudaEventDestroy(e->ev_rew[i]);
   }
   if (e->side) cudaStreamDestroy(e->side);
+  if (e->graph) cudaGraphExecDestroy(e->graph);
+  if (e->copy) cudaStreamDestroy(e->copy);
+  if (e->ev_host) cudaEventDestroy(e->ev_host);
+  for (cudaEvent_t ev : e->hs_events) cudaEventDestroy(ev);
+  if (e->hs_actions) cudaFree(e->hs_actions);
+  if (e->hs_reward) cudaFree(e->hs_reward);
+  if (e->hs_done) cudaFree(e->hs_done);
   for (auto& t : e->timed) {  // kernel timing enabled but never polled
     cudaEventDestroy(t.a);
     cudaEventDestroy(t.b);
@@ -718,6 +794,7 @@ int pcb_generate_instances_device(pcb_env_t* e, const int32_t gen[12], uint64_t 
   const size_t bytes = (size_t)count * e->d.L.rec_stride;
   if (!e->bank || e->bank_count != (uint32_t)count) {
     CU(cudaStreamSynchronize((cudaStream_t)stream));  // nobody may still read the old bank
+    if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
     if (e->bank) { cudaFree(e->bank); e->bank = nullptr; }
     void* p = nullptr;
     CU(cudaMalloc(&p, bytes));
@@ -799,7 +876,8 @@ static int rollout_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_ac
 // double-buffered result tensors (pcb_rollout_random_logged)
 static int step_impl(pcb_env_t* e, const int32_t* d_actions, int action_format, uint64_t seed,
                      int32_t* d_next_actions, void* stream, bool overlap,
-                     double* reward_row = nullptr, uint8_t* done_row = nullptr) {
+                     double* reward_row = nullptr, uint8_t* done_row = nullptr,
+                     const uint64_t* step_base = nullptr) {
   int rc = ready(e);
   if (rc) return rc;
   if (!d_actions) return fail(PCB_ERR_INVALID, "d_actions is NULL");
@@ -822,6 +900,7 @@ static int step_impl(pcb_env_t* e, const int32_t* d_actions, int action_format, 
   p.action_format = action_format;
   p.seed = seed;
   p.actions_out = d_next_actions;
+  p.step_base = step_base;
   if (reward_row) p.out.reward = reward_row;
   if (done_row) p.out.done = done_row;
   rc = launch(e, K_STEP, p, st);
@@ -878,9 +957,15 @@ int pcb_step_host(pcb_env_t* e, const int32_t* h_actions, int action_format, dou
   CU(cudaMemcpyAsync(e->d_actions, h_actions, (size_t)e->n_envs * per * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   rc = pcb_step(e, e->d_actions, action_format, stream);
   if (rc) return rc;
-  const size_t half = (size_t)((e->step_no + 1) & 1) * e->n_envs;  // the half the step just wrote
-  CU(cudaMemcpyAsync(h_reward, e->base.reward + half, (size_t)e->n_envs * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(h_done, e->base.done + half, (size_t)e->n_envs, cudaMemcpyDeviceToHost, st));
+  // the half the step just wrote: [reward f64 x N | done u8 x N] contiguous on the device
+  const size_t N = (size_t)e->n_envs;
+  const uint8_t* blk = reinterpret_cast<const uint8_t*>(e->base.reward) + (size_t)((e->step_no + 1) & 1) * e->res_stride;
+  if (h_done == reinterpret_cast<uint8_t*>(h_reward + N)) {  // packed host buffer: one copy
+    CU(cudaMemcpyAsync(h_reward, blk, N * 9, cudaMemcpyDeviceToHost, st));
+  } else {
+    CU(cudaMemcpyAsync(h_reward, blk, N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_done, blk + N * sizeof(double), N, cudaMemcpyDeviceToHost, st));
+  }
   CU(cudaStreamSynchronize(st));
   return 0;
 }
@@ -899,6 +984,13 @@ int pcb_get_tensor(pcb_env_t* e, const char* key, DLManagedTensor** out) {
     m->dl_tensor.dtype = DLDataType{(uint8_t)t.code, (uint8_t)t.bits, 1};
     m->dl_tensor.shape = shape;
     m->dl_tensor.strides = nullptr;
+    if (!t.strides.empty()) {  // shape and strides share one allocation (freed by the deleter)
+      int64_t* both = (int64_t*)realloc(shape, sizeof(int64_t) * 2 * t.shape.size());
+      if (!both) { free(m); free(shape); return fail(PCB_ERR_NOMEM, "out of host memory"); }
+      for (size_t i = 0; i < t.shape.size(); ++i) both[t.shape.size() + i] = t.strides[i];
+      m->dl_tensor.shape = both;
+      m->dl_tensor.strides = both + t.shape.size();
+    }
     m->dl_tensor.byte_offset = 0;
     m->manager_ctx = nullptr;
     m->deleter = dl_deleter;
@@ -992,6 +1084,8 @@ static int rollout_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_ac
   p.base = e->base;
   p.state = e->state; p.bank = e->bank; p.ratio_lut = e->ratio_lut; p.stats = e->stats;
   p.actions = d_actions; p.action_format = action_format;
+  p.action_stride = d_actions ? (size_t)e->n_envs * (action_format == PCB_ACTION_FLAT ? 1 : (e->d.kind == 0 ? 2 : 3)) : 0;
+  p.res_stride = (uint32_t)e->res_stride;
   p.actions_log = d_actions_log;
   p.reward_log = d_reward_log; p.done_log = d_done_log;
   p.seed = seed; p.step_no = e->step_no; p.bank_count = e->bank_count;
@@ -1021,6 +1115,90 @@ static int rollout_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_ac
   return 0;
 }
 
+static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
+
+// pcb_rollout_random of the per-step kinds as CUDA-graph replays.  One graph = L consecutive
+// steps with L a multiple of the observation ring, of the 4 job counters and of 2 (result
+// halves, action ping-pong): after L steps every pointer a launch carries is the same
+// again, so the captured graph can be replayed as is.  The one thing that must keep moving
+// -- the step counter of the random policy -- is read from device memory (Params::step_base)
+// and advanced by the last node.  *done_steps = steps executed here (a multiple of L); the
+// caller runs the remainder with plain launches.  Actions of the first step: d_actions.
+static int rollout_graphed(pcb_env_t* e, uint64_t seed, int n_steps, cudaStream_t st, int* done_steps) {
+  *done_steps = 0;
+  if (!e->use_graph || e->timing || e->fused) return 0;
+  // the default streams cannot be captured
+  if (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) return 0;
+  const int base = e->ring * 4 / gcd_i(e->ring, 4);  // lcm(ring, 4)
+  if (base > 128 || n_steps < base) return 0;
+  const int L = base * std::max(1, 16 / base);       // at least ~16 steps per launch
+  if (n_steps < L) return 0;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return 0;  // the caller is capturing this stream itself
+  }
+  const bool overlap = e->overlap && e->d.kind >= 2;
+  const bool reuse = e->graph && e->graph_len == L && e->graph_slice == e->slice &&
+                     e->graph_next_step == e->step_no && e->graph_seed == seed &&
+                     e->graph_stream == st && e->graph_overlap == overlap;
+  if (!reuse) {
+    if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
+    int rc = join_rewards(e, st);  // no event of an earlier, un-captured launch may be waited on
+    if (rc) return rc;
+    CU(cudaMemsetAsync(e->d_step_base, 0, sizeof(uint64_t), st));
+    const uint64_t step0 = e->step_no;
+    const int slice0 = e->slice;
+    const int64_t launches0 = e->launches;
+    CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    int32_t* cur = e->d_actions;
+    for (int t = 0; t < L && rc == 0; ++t) {
+      int32_t* nxt = cur == e->d_actions ? e->d_actions2 : e->d_actions;
+      rc = step_impl(e, cur, PCB_ACTION_TUPLE, seed, nxt, st, overlap, nullptr, nullptr, e->d_step_base);
+      cur = nxt;
+    }
+    if (rc == 0) rc = join_rewards(e, st);
+    if (rc == 0) {
+      advance_step_base_kernel<<<1, 1, 0, st>>>(e->d_step_base, (uint64_t)L);
+      if (cudaGetLastError() != cudaSuccess) rc = fail(PCB_ERR_CUDA, "advance_step_base_kernel launch failed");
+    }
+    cudaGraph_t g = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(st, &g);
+    // capture only records: put the host-side bookkeeping back to where the handle really is
+    e->step_no = step0; e->slice = slice0;
+    e->graph_launches = e->launches - launches0 + 1;
+    e->launches = launches0;
+    e->rew_pending[0] = e->rew_pending[1] = false;
+    if (rc || ce != cudaSuccess || !g) {
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+      e->use_graph = false;  // this configuration cannot be captured: plain launches from now on
+      return rc ? rc : 0;
+    }
+    ce = cudaGraphInstantiate(&e->graph, g, 0);
+    cudaGraphDestroy(g);
+    if (ce != cudaSuccess) {
+      e->graph = nullptr; e->use_graph = false;
+      cudaGetLastError();
+      return 0;
+    }
+    e->graph_len = L; e->graph_slice = slice0; e->graph_seed = seed; e->graph_stream = st;
+    e->graph_overlap = overlap;
+  }
+  while (n_steps - *done_steps >= L) {
+    CU(cudaGraphLaunch(e->graph, st));
+    e->step_no += (uint64_t)L;  // L is a multiple of the ring: the slice index is unchanged
+    e->launches += e->graph_launches;
+    e->graph_replays += 1;
+    *done_steps += L;
+  }
+  e->graph_next_step = e->step_no;
+  return 0;
+}
+
+static int restore_result_halves(pcb_env_t* e, int n_steps, const double* d_reward_log,
+                                 const uint8_t* d_done_log, cudaStream_t st);
+
 int pcb_rollout_random_logged(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_actions_log,
                               double* d_reward_log, uint8_t* d_done_log, void* stream) {
   int rc = ready(e);
@@ -1036,6 +1214,14 @@ int pcb_rollout_random_logged(pcb_env_t* e, uint64_t seed, int n_steps, int32_t*
   int32_t* cur = d_actions_log ? d_actions_log : e->d_actions;
   rc = pcb_sample_random_actions(e, seed, cur, stream);
   if (rc) return rc;
+  if (!d_actions_log && !d_reward_log && !d_done_log) {
+    int done_steps = 0;
+    rc = rollout_graphed(e, seed, n_steps, (cudaStream_t)stream, &done_steps);
+    if (rc) return rc;
+    if (done_steps == n_steps) return 0;
+    n_steps -= done_steps;  // the rest (less than one graph) with per-step launches
+    // a graph ends with the actions of its successor in d_actions, as the sampler left them
+  }
   for (int t = 0; t < n_steps; ++t) {
     int32_t* nxt = nullptr;
     if (t + 1 < n_steps)
@@ -1049,22 +1235,128 @@ int pcb_rollout_random_logged(pcb_env_t* e, uint64_t seed, int n_steps, int32_t*
   }
   rc = join_rewards(e, (cudaStream_t)stream);
   if (rc) return rc;
-  // the result tensors ([2, N], by step parity) still describe the last two steps
-  cudaStream_t st = (cudaStream_t)stream;
+  return restore_result_halves(e, n_steps, d_reward_log, d_done_log, (cudaStream_t)stream);
+}
+
+// the result tensors ([2] halves by step parity) describe the last two steps: copy them back
+// from the [T, N] logs the steps wrote into
+static int restore_result_halves(pcb_env_t* e, int n_steps, const double* d_reward_log,
+                                 const uint8_t* d_done_log, cudaStream_t st) {
+  const size_t N = (size_t)e->n_envs;
   for (int back = 0; back < 2 && back < n_steps; ++back) {
     const size_t t = (size_t)(n_steps - 1 - back);
-    const size_t half = (size_t)((e->step_no - 1 - back) & 1) * N;
+    const size_t half = (size_t)((e->step_no - 1 - back) & 1) * e->res_stride;
     if (d_reward_log)
-      CU(cudaMemcpyAsync(e->base.reward + half, d_reward_log + t * N, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      CU(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(e->base.reward) + half, d_reward_log + t * N,
+                         N * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (d_done_log)
       CU(cudaMemcpyAsync(e->base.done + half, d_done_log + t * N, N, cudaMemcpyDeviceToDevice, st));
   }
   return 0;
 }
 
+constexpr int kHostChunk = 8;  // pcb_steps_host uploads the action rows in chunks of 8 steps
+
+static int ensure_host_staging(pcb_env_t* e, size_t steps) {
+  if (steps <= e->hs_steps) return 0;
+  CU(cudaDeviceSynchronize());
+  if (e->hs_actions) cudaFree(e->hs_actions);
+  if (e->hs_reward) cudaFree(e->hs_reward);
+  if (e->hs_done) cudaFree(e->hs_done);
+  e->hs_actions = nullptr; e->hs_reward = nullptr; e->hs_done = nullptr; e->hs_steps = 0;
+  const size_t N = (size_t)e->n_envs;
+  void* p = nullptr;
+  cudaError_t err = cudaMalloc(&p, steps * N * 3 * sizeof(int32_t));
+  if (err == cudaSuccess) { e->hs_actions = (int32_t*)p; err = cudaMalloc(&p, steps * N * sizeof(double)); }
+  if (err == cudaSuccess) { e->hs_reward = (double*)p; err = cudaMalloc(&p, steps * N); }
+  if (err == cudaSuccess) e->hs_done = (uint8_t*)p;
+  if (err != cudaSuccess)
+    return fail(err == cudaErrorMemoryAllocation ? PCB_ERR_NOMEM : PCB_ERR_CUDA,
+                "pcb_steps_host staging for %zu steps: %s", steps, cudaGetErrorString(err));
+  e->hs_steps = steps;
+  if (!e->copy) CU(cudaStreamCreateWithFlags(&e->copy, cudaStreamNonBlocking));
+  if (!e->ev_host) CU(cudaEventCreateWithFlags(&e->ev_host, cudaEventDisableTiming));
+  return 0;
+}
+
+int pcb_steps_host(pcb_env_t* e, const int32_t* h_actions, int n_steps, int action_format,
+                   double* h_reward, uint8_t* h_done, void* stream) {
+  int rc = ready(e);
+  if (rc) return rc;
+  if (!h_actions || !h_reward || !h_done) return fail(PCB_ERR_INVALID, "NULL host buffer");
+  if (n_steps < 0) return fail(PCB_ERR_INVALID, "n_steps must be >= 0");
+  if (action_format != PCB_ACTION_TUPLE && action_format != PCB_ACTION_FLAT)
+    return fail(PCB_ERR_INVALID, "unknown action format %d", action_format);
+  if (n_steps == 0) return 0;
+  CU(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t N = (size_t)e->n_envs, T = (size_t)n_steps;
+  const size_t per = N * (action_format == PCB_ACTION_FLAT ? 1 : (e->d.kind == 0 ? 2 : 3));
+  rc = ensure_host_staging(e, T);
+  if (rc) return rc;
+  if (e->fused) {
+    // pin-less kinds: every row up, ONE launch of the multi-step kernel, every result down
+    CU(cudaMemcpyAsync(e->hs_actions, h_actions, T * per * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    rc = rollout_fused(e, 0, n_steps, nullptr, e->hs_reward, e->hs_done, st, e->hs_actions, action_format);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(h_reward, e->hs_reward, T * N * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(h_done, e->hs_done, T * N, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return 0;
+  }
+  // Pin kinds: one step + one reward kernel per row.  The action rows travel on a copy
+  // stream in chunks (the first step starts after the first chunk, not after all rows); the
+  // results of step t leave on the stream its reward kernel ran on, while step t+1 runs.
+  const size_t chunks = (T + kHostChunk - 1) / kHostChunk;
+  while (e->hs_events.size() < chunks) {
+    cudaEvent_t ev = nullptr;
+    CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    e->hs_events.push_back(ev);
+  }
+  CU(cudaEventRecord(e->ev_host, st));           // the copy stream starts after the caller's work
+  CU(cudaStreamWaitEvent(e->copy, e->ev_host, 0));
+  for (size_t c = 0; c < chunks; ++c) {
+    const size_t t0 = c * kHostChunk, nt = std::min((size_t)kHostChunk, T - t0);
+    CU(cudaMemcpyAsync(e->hs_actions + t0 * per, h_actions + t0 * per, nt * per * sizeof(int32_t),
+                       cudaMemcpyHostToDevice, e->copy));
+    CU(cudaEventRecord(e->hs_events[c], e->copy));
+  }
+  const bool routes = e->d.kind >= 2;
+  const bool overlap = routes && e->overlap;
+  for (size_t t = 0; t < T; ++t) {
+    if (t % kHostChunk == 0) CU(cudaStreamWaitEvent(st, e->hs_events[t / kHostChunk], 0));
+    double* rrow = e->hs_reward + t * N;
+    uint8_t* drow = e->hs_done + t * N;
+    rc = step_impl(e, e->hs_actions + t * per, action_format, 0, nullptr, stream, overlap, rrow, drow);
+    if (rc) return rc;
+    cudaStream_t out = overlap ? e->side : st;   // the stream on which row t becomes final
+    CU(cudaMemcpyAsync(h_reward + t * N, rrow, N * sizeof(double), cudaMemcpyDeviceToHost, out));
+    CU(cudaMemcpyAsync(h_done + t * N, drow, N, cudaMemcpyDeviceToHost, out));
+  }
+  if (overlap) {
+    rc = join_rewards(e, st);
+    if (rc) return rc;
+    CU(cudaEventRecord(e->ev_host, e->side));    // ... and the copies queued behind them
+    CU(cudaStreamWaitEvent(st, e->ev_host, 0));
+  }
+  rc = restore_result_halves(e, n_steps, e->hs_reward, e->hs_done, st);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(st));
+  return 0;
+}
+
 int pcb_rollout_random(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_actions_log, void* stream) {
   return pcb_rollout_random_logged(e, seed, n_steps, d_actions_log, nullptr, nullptr, stream);
 }
+
+int pcb_set_graph_rollout(pcb_env_t* e, int on) {
+  if (!e) return fail(PCB_ERR_INVALID, "env is NULL");
+  e->use_graph = on != 0;
+  if (!on && e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
+  return 0;
+}
+
+int64_t pcb_graph_replays(pcb_env_t* e) { return e ? e->graph_replays : 0; }
 
 int pcb_set_reward_overlap(pcb_env_t* e, int on) {
   if (!e) return fail(PCB_ERR_INVALID, "env is NULL");

@@ -29,11 +29,12 @@ constexpr unsigned kFull = 0xffffffffu;
 #define PCB_LAYOUT_FIELDS(X)                                                                   \
   X(O) X(P) X(F) X(st_comps) X(st_pins) X(st_occ) X(st_orient) X(st_stride) X(rec_comps) X(rec_pins)        \
   X(rec_stride) X(grid_b) X(mask_b) X(feat_n) X(pnum_n) X(pcat_n) X(pgrid_b) X(cgrid_b)        \
-  X(sm_mrow) X(sm_stage) X(sm_scr) X(sm_stride) X(pchunk)
+  X(sm_mrow) X(sm_stage) X(sm_scr) X(sm_stride) X(sm_bulk) X(pchunk)
 
 template <int KIND, int HH, int WW, int CC, int MH, int MW, int KK, int MAXPINS>
 struct FixedShape {
   static constexpr bool fixed = true;
+  static constexpr int kH = HH;
   static constexpr bool fast_board = HH == WW && (HH == 16 || HH == 32 || HH == 64);
   static constexpr Layout LL = make_layout(KIND, HH, WW, CC, MH, MW, KK, MAXPINS, fast_board);
   __device__ __forceinline__ explicit FixedShape(const Dims&) {}
@@ -53,6 +54,7 @@ struct FixedShape {
 
 struct DynShape {
   static constexpr bool fixed = false;
+  static constexpr int kH = 0;
   const Dims& d;
   __device__ __forceinline__ explicit DynShape(const Dims& dd) : d(dd) {}
   __device__ __forceinline__ int kind() const { return d.kind; }
@@ -184,6 +186,72 @@ __device__ __forceinline__ void copy16(void* dst, const void* src, int nbytes, i
   const uint4* s = reinterpret_cast<const uint4*>(src);
   uint4* d = reinterpret_cast<uint4*>(dst);
   for (int i = lane; i < (nbytes >> 4); i += 32) d[i] = s[i];
+}
+
+// ---------------------------------------------------------------------------
+// Bulk-copy write-out (sm_90+ bulk async copies, no tensor map): one thread hands a
+// contiguous, 16-byte aligned run of shared memory to the copy engine, which writes it to
+// global memory without occupying load/store slots of the SM.  The stores carry the same
+// evict-first L2 policy as st.global.cs (st_stream above).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// generic-proxy writes to shared memory (st.shared) -> visible to the async proxy
+__device__ __forceinline__ void fence_smem_for_bulk() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t nbytes, uint64_t pol) {
+  const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+               :: "l"(gdst), "r"(s), "r"(nbytes), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the copy engine has READ every committed source buffer (they may be reused / the CTA may exit)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------
+// The per-env state records are the one thing every step re-reads: 29 MB at 65 536 envs of
+// config C, written by step t and read by step t+1 ~90 us later, after ~500 MB of observation
+// bytes have streamed through the 126 MB L2; ncu shows 33 MB of DRAM reads per launch, i.e.
+// every record comes back from DRAM, and the first use of the loaded record is the top stall.
+// PCB_OPT_STATE_L2=1 gives their loads and stores an L2 evict_last policy.  Measured (round 2,
+// profiles/README.md): step kernel alone 86.2 -> 89.0 us, whole step 0.819 -> 0.790 -- slower,
+// so it is off; the code stays as the record of the experiment.
+// ---------------------------------------------------------------------------
+#ifndef PCB_OPT_STATE_L2
+#define PCB_OPT_STATE_L2 0
+#endif
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint4 ld_state(const void* p) {
+#if PCB_OPT_STATE_L2
+  uint4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(l2_evict_last_policy()));
+  return v;
+#else
+  return *reinterpret_cast<const uint4*>(p);
+#endif
+}
+__device__ __forceinline__ void st_state(void* p, uint4 v) {
+#if PCB_OPT_STATE_L2
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(l2_evict_last_policy()) : "memory");
+#else
+  *reinterpret_cast<uint4*>(p) = v;
+#endif
+}
+// shared -> global copy of a state record
+__device__ __forceinline__ void store_state(void* gdst, const void* ssrc, int nbytes, int lane) {
+  const uint4* s4 = reinterpret_cast<const uint4*>(ssrc);
+  uint4* d = reinterpret_cast<uint4*>(gdst);
+  for (int i = lane; i < (nbytes >> 4); i += 32) st_state(d + i, s4[i]);
 }
 
 // ---------------------------------------------------------------------------
@@ -600,6 +668,14 @@ __device__ __forceinline__ float area_ratio(const S& sh, const Params& p, int ar
   return p.ratio_lut[area];
 }
 
+// step number the random policy draws with (see Params::step_base)
+__device__ __forceinline__ uint64_t policy_step(const Params& p) {
+  return p.step_no + (p.step_base ? *p.step_base : 0ull);
+}
+
+// last node of a captured rollout graph: the next replay is `n` steps further on
+__global__ void advance_step_base_kernel(uint64_t* step_base, uint64_t n) { *step_base += n; }
+
 // ---------------------------------------------------------------------------
 // observation write-out (everything the reference copies into the obs dict:
 // rect:410-416, pin:1680-1687, spatial:1633-1644; layout SURVEY.md Appendix C)
@@ -625,9 +701,36 @@ __device__ __forceinline__ void write_obs(const S& sh, const Params& p, Env<T>& 
   uint32_t* flat = reinterpret_cast<uint32_t*>(e.scr);
   write_board<RPL, T, S>(sh, p.out.grid + (size_t)env * sh.grid_b(), occ, e.occ, flat, lane, 0, lut);
   uint8_t* mk = p.out.mask + (size_t)env * sh.mask_b();
-  write_board<RPL, T, S>(sh, mk, m0, e.mrow, flat, lane, O == 4 ? 2 * HW : 0, lut);
-  if (O >= 2)
-    write_board<RPL, T, S>(sh, mk + HW, m1, e.mrow + rows, flat, lane, O == 4 ? 2 * HW : 0, lut);
+  bool bulk = false;
+  uint64_t pol = 0;
+  if constexpr (S::fixed && RPL == 1 && sizeof(T) == 4) {
+    if (sh.sm_bulk() != 0) {
+      // 32x32 pin shapes: mask rows of orientation 0 | 1 -> 2 KB of bytes in shared memory,
+      // then the copy engine writes them to orientations 0,1 and again to 2,3 (pin:1868-1869)
+      bulk = true;
+      pol = l2_evict_first_policy();
+      uint4* sb = reinterpret_cast<uint4*>(e.sm + sh.sm_bulk());
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int src = (lane >> 1) + 16 * half, sft = 16 * (lane & 1);
+        const uint32_t w0 = __shfl_sync(kFull, (uint32_t)m0[0], src);
+        const uint32_t w1 = __shfl_sync(kFull, (uint32_t)m1[0], src);
+        sb[half * 32 + lane] = expand16(lut, w0 >> sft);
+        sb[64 + half * 32 + lane] = expand16(lut, w1 >> sft);
+      }
+      fence_smem_for_bulk();
+      __syncwarp();
+      if (lane == 0) {
+        bulk_store(mk, sb, 2 * 1024, pol);
+        bulk_store(mk + 2 * 1024, sb, 2 * 1024, pol);
+      }
+    }
+  }
+  if (!bulk) {
+    write_board<RPL, T, S>(sh, mk, m0, e.mrow, flat, lane, O == 4 ? 2 * HW : 0, lut);
+    if (O >= 2)
+      write_board<RPL, T, S>(sh, mk + HW, m1, e.mrow + rows, flat, lane, O == 4 ? 2 * HW : 0, lut);
+  }
   const int kind = sh.kind();
   if (kind == 0) return;
 
@@ -717,11 +820,23 @@ __device__ __forceinline__ void write_obs(const S& sh, const Params& p, Env<T>& 
         *reinterpret_cast<uint2*>(snum + row * 4) = v;
         scat[row] = pr.net;
       }
-      __syncwarp();
-      copy_out(p.out.pnum + (size_t)env * pnum_n + c0 * P * 4, snum, rows * 8, lane);
-      copy_out(p.out.pcat + (size_t)env * pcat_n + c0 * P, scat, rows * 2, lane);
-      __syncwarp();
+      if (bulk && pchunk == C && ((rows * 2) & 15) == 0) {
+        // the whole slice of both pin tensors in one pass: two bulk copies instead of ~5
+        // shared-memory loads + 16-byte stores per lane
+        fence_smem_for_bulk();
+        __syncwarp();
+        if (lane == 0) {
+          bulk_store(p.out.pnum + (size_t)env * pnum_n, snum, rows * 8, pol);
+          bulk_store(p.out.pcat + (size_t)env * pcat_n, scat, rows * 2, pol);
+        }
+      } else {
+        __syncwarp();
+        copy_out(p.out.pnum + (size_t)env * pnum_n + c0 * P * 4, snum, rows * 8, lane);
+        copy_out(p.out.pcat + (size_t)env * pcat_n + c0 * P, scat, rows * 2, lane);
+        __syncwarp();
+      }
     }
+    if (bulk && lane == 0) bulk_commit();
     return;
   }
   if (kind == 3) {
@@ -807,6 +922,7 @@ __device__ __forceinline__ void write_obs(const S& sh, const Params& p, Env<T>& 
   __syncwarp();
   copy_out(p.out.cgrid + (size_t)env * sh.cgrid_b(), e.stage, sh.cgrid_b(), lane);
   __syncwarp();
+  if (bulk && lane == 0) bulk_commit();
 }
 
 // Mask rows of the component to place next (both orientations); zero when none is left
@@ -1091,7 +1207,7 @@ __device__ __forceinline__ void finish_episode(const S& sh, const Params& p, Env
   if (!d.autoreset) {
     if (lane == 0 && first_report) {
       e.hdr->flags |= kFlagFinished;
-      *reinterpret_cast<uint4*>(gstate) = *reinterpret_cast<const uint4*>(e.sm);
+      st_state(gstate, *reinterpret_cast<const uint4*>(e.sm));
     }
     return;
   }
@@ -1105,51 +1221,47 @@ __device__ __forceinline__ void finish_episode(const S& sh, const Params& p, Env
 #pragma unroll
   for (int k = 0; k < RPL; ++k) occ[k] = T(0);
   next_masks<RPL, T, S>(sh, d, e, occ, 0, e.hdr->n_comp, lane, m0, m1);
-  copy16(gstate, e.sm, sh.st_stride(), lane);
+  store_state(gstate, e.sm, sh.st_stride(), lane);
   write_obs<RPL, T, S>(sh, p, e, env, lane, occ, m0, m1);
   if (p.actions_out)
-    sample_action<RPL, T, S>(sh, m0, m1, p.seed, env, p.step_no + 1, lane, p.actions_out);
+    sample_action<RPL, T, S>(sh, m0, m1, p.seed, env, policy_step(p) + 1, lane, p.actions_out);
 }
 
 // ---------------------------------------------------------------------------
 // K1/K2/K3 (+ fused K4/K6/K7): step
 // ---------------------------------------------------------------------------
-template <int RPL, typename T, typename S>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, PCB_MIN_BLOCKS)
-step_kernel(const Params p) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  const Dims& d = p.d;
-  const S sh(d);
-  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
-  const int env = blockIdx.x * kWarpsPerCta + wic;
-  const bool live = env < p.n_envs;
-  // issue every global load of this warp before anything waits: table, state, action
-  const uint4 lut_part = expand_lut_fetch();
-  const uint8_t* gstate_c = p.state + (size_t)(live ? env : 0) * sh.st_stride();
-  const int n16 = sh.st_stride() >> 4;
-  uint4 st0 = make_uint4(0, 0, 0, 0);
-  if (lane < n16) st0 = reinterpret_cast<const uint4*>(gstate_c)[lane];
-  const int kind = sh.kind();
-  int o = 0, x = 0, y = 0;
-  if (live) {  // FlatteningActionWrapper*: env_wrappers.py:80-98, wrapper_square.py:54-69
-    if (p.action_format == 1) {
-      int a = p.actions[env];
-      int hw = sh.H() * sh.W();
-      if (a < 0) { o = -1; }
-      else { o = a / hw; int rem = a - o * hw; x = rem / sh.W(); y = rem - x * sh.W(); }
-    } else if (kind == 0) {
-      x = p.actions[2 * env]; y = p.actions[2 * env + 1];
-    } else {
-      o = p.actions[3 * env]; x = p.actions[3 * env + 1]; y = p.actions[3 * env + 2];
-    }
+#ifndef PCB_OPT_PERSIST
+#define PCB_OPT_PERSIST 0
+#endif
+// the action of one env as (o, x, y): tuple or flat (FlatteningActionWrapper*:
+// env_wrappers.py:80-98, wrapper_square.py:54-69)
+template <typename S>
+__device__ __forceinline__ void load_action(const S& sh, const Params& p, int env, int& o, int& x, int& y) {
+  o = 0; x = 0; y = 0;
+  if (p.action_format == 1) {
+    int a = p.actions[env];
+    int hw = sh.H() * sh.W();
+    if (a < 0) { o = -1; }
+    else { o = a / hw; int rem = a - o * hw; x = rem / sh.W(); y = rem - x * sh.W(); }
+  } else if (sh.kind() == 0) {
+    x = p.actions[2 * env]; y = p.actions[2 * env + 1];
+  } else {
+    o = p.actions[3 * env]; x = p.actions[3 * env + 1]; y = p.actions[3 * env + 2];
   }
-  expand_lut_store(smem, lut_part);
-  if (!live) return;
-  Env<T> e(smem + kLutBytes + (size_t)wic * sh.sm_stride(), sh);
+}
+
+// one environment, one warp: everything of step() after the state chunk st0 (lane's 16
+// bytes of the record) and the action have been requested
+template <int RPL, typename T, typename S>
+__device__ __forceinline__ void step_env(const S& sh, const Params& p, Env<T>& e, int env, int lane,
+                                         uint4 st0, int o, int x, int y) {
+  const Dims& d = p.d;
+  const int kind = sh.kind();
+  const int n16 = sh.st_stride() >> 4;
   uint8_t* gstate = p.state + (size_t)env * sh.st_stride();
   if (lane < n16) reinterpret_cast<uint4*>(e.sm)[lane] = st0;
   for (int i = 32 + lane; i < n16; i += 32)
-    reinterpret_cast<uint4*>(e.sm)[i] = reinterpret_cast<const uint4*>(gstate)[i];
+    reinterpret_cast<uint4*>(e.sm)[i] = ld_state(reinterpret_cast<const uint4*>(gstate) + i);
   __syncwarp();
 
   T occ[RPL];
@@ -1232,15 +1344,15 @@ step_kernel(const Params p) {
   if (!restart) {  // a restarting env overwrites its state below
     uint4* g4 = reinterpret_cast<uint4*>(gstate);
     const uint4* s4 = reinterpret_cast<const uint4*>(e.sm);
-    if (lane < 2) g4[lane] = s4[lane];
+    if (lane < 2) st_state(g4 + lane, s4[lane]);
     if (valid)
-      for (int i = 2 + lane; i < (sh.st_stride() >> 4); i += 32) g4[i] = s4[i];
+      for (int i = 2 + lane; i < (sh.st_stride() >> 4); i += 32) st_state(g4 + i, s4[i]);
   }
 
   if (!restart) {
     write_obs<RPL, T, S>(sh, p, e, env, lane, occ, m0, m1);
     if (p.actions_out)  // a finished, not restarting env has no valid action: reports (0,0,0)
-      sample_action<RPL, T, S>(sh, m0, m1, p.seed, env, p.step_no + 1, lane, p.actions_out);
+      sample_action<RPL, T, S>(sh, m0, m1, p.seed, env, policy_step(p) + 1, lane, p.actions_out);
   }
   if (lane == 0) {
     p.out.done[env] = done ? 1 : 0;
@@ -1250,6 +1362,46 @@ step_kernel(const Params p) {
     }
   }
   if (done) finish_episode<RPL, T, S>(sh, p, e, env, lane, reward, route, gstate);
+  // shared memory handed to the copy engine must stay in place until it has been read
+}
+
+template <int RPL, typename T, typename S>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, PCB_MIN_BLOCKS)
+step_kernel(const Params p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const Dims& d = p.d;
+  const S sh(d);
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  const int n16 = sh.st_stride() >> 4;
+  Env<T> e(smem + kLutBytes + (size_t)wic * sh.sm_stride(), sh);
+#if PCB_OPT_PERSIST
+  // persistent CTAs: the grid fills the machine once and every warp walks over its share of
+  // the environments, so the expansion table is built once per CTA instead of once per 4 envs
+  build_expand_lut(smem);
+  for (int env = blockIdx.x * kWarpsPerCta + wic; env < p.n_envs; env += gridDim.x * kWarpsPerCta) {
+    uint4 st0 = make_uint4(0, 0, 0, 0);
+    if (lane < n16) st0 = ld_state(reinterpret_cast<const uint4*>(p.state + (size_t)env * sh.st_stride()) + lane);
+    int o, x, y;
+    load_action(sh, p, env, o, x, y);
+    step_env<RPL, T, S>(sh, p, e, env, lane, st0, o, x, y);
+    // shared memory handed to the copy engine must stay in place until it has been read
+    if constexpr (S::fixed) if (sh.sm_bulk() != 0 && lane == 0) bulk_wait_read();
+    __syncwarp();
+  }
+#else
+  const int env = blockIdx.x * kWarpsPerCta + wic;
+  const bool live = env < p.n_envs;
+  // issue every global load of this warp before anything waits: table, state, action
+  const uint4 lut_part = expand_lut_fetch();
+  uint4 st0 = make_uint4(0, 0, 0, 0);
+  if (lane < n16) st0 = ld_state(reinterpret_cast<const uint4*>(p.state + (size_t)(live ? env : 0) * sh.st_stride()) + lane);
+  int o = 0, x = 0, y = 0;
+  if (live) load_action(sh, p, env, o, x, y);
+  expand_lut_store(smem, lut_part);
+  if (!live) return;
+  step_env<RPL, T, S>(sh, p, e, env, lane, st0, o, x, y);
+  if constexpr (S::fixed) if (sh.sm_bulk() != 0 && lane == 0) bulk_wait_read();
+#endif
 }
 
 // K4: the routing reward (find_reward, pin:832-975) of the episodes that finished in this
@@ -1343,12 +1495,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) reset_kernel(const Params p
 #pragma unroll
   for (int k = 0; k < RPL; ++k) occ[k] = T(0);
   next_masks<RPL, T, S>(sh, d, e, occ, 0, e.hdr->n_comp, lane, m0, m1);
-  copy16(gstate, e.sm, sh.st_stride(), lane);
+  store_state(gstate, e.sm, sh.st_stride(), lane);
   write_obs<RPL, T, S>(sh, p, e, env, lane, occ, m0, m1);
   if (lane == 0) {
     p.out.done[env] = 0;
     p.out.reward[env] = 0.0;
   }
+  if constexpr (S::fixed) if (sh.sm_bulk() != 0 && lane == 0) bulk_wait_read();
 }
 
 // K7 as a stand-alone launch (pcb_sample_random_actions): masks recomputed from the state.

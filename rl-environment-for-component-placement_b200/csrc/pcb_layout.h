@@ -88,6 +88,7 @@ struct Layout {
   int rec_comps, rec_pins, rec_stride;
   int grid_b, mask_b, feat_n, pnum_n, pcat_n, pgrid_b, cgrid_b;
   int sm_mrow, sm_stage, sm_scr, sm_stride;
+  int sm_bulk;   // offset of the mask staging of the bulk-copy write-out, 0 = not used
   int pchunk;  // pin env: components whose pin feature rows are staged per pass
 };
 
@@ -106,6 +107,17 @@ PCB_HD constexpr int pin_chunk_comps(int C, int P) {
   if (C * P * 10 <= 3584) return C;
   const int by_size = 8 * maxc(1, 2048 / (P * 80));
   return by_size < C ? by_size : C;
+}
+
+// PCB_OPT_BULK: the 32x32 pin shapes stage one env's action-mask rows (orientation 0 | 1, 2 KB)
+// in shared memory and hand them to the bulk-copy engine (cp.async.bulk.global.shared::cta,
+// SASS UBLKCP) -- twice, because orientations 2, 3 repeat 0, 1 -- instead of 8 x 512-byte
+// st.global per warp; the pin feature rows leave the same way.
+#ifndef PCB_OPT_BULK
+#define PCB_OPT_BULK 0
+#endif
+PCB_HD constexpr bool bulk_shape(int kind, int H, int W, bool fast_board) {
+  return PCB_OPT_BULK != 0 && fast_board && kind >= 2 && H == 32 && W == 32;
 }
 
 // fast_board: the kernel expands bitboards straight from registers (FixedShape 16/32/64
@@ -144,6 +156,11 @@ PCB_HD constexpr Layout make_layout(int kind, int H, int W, int C, int mh, int m
   L.sm_scr = L.sm_mrow + (fast_board ? 0 : 2 * rows * word);
   L.sm_stage = L.sm_scr + (fast_board ? 0 : align16c(4 * ((H * W + 31) / 32 + 3)));
   L.sm_stride = align16c(L.sm_stage + align16c(stage) + 16);
+  L.sm_bulk = 0;
+  if (bulk_shape(kind, H, W, fast_board)) {
+    L.sm_bulk = L.sm_stride;
+    L.sm_stride += 2 * H * W;
+  }
   return L;
 }
 
@@ -212,6 +229,10 @@ struct Params {
   uint64_t seed;
   uint64_t step_no;
   int32_t* actions_out;  // != nullptr: also sample the next random action of every env
+  // CUDA-graph replays: a captured launch carries the step number of capture time; the steps
+  // taken since then (a multiple of the graph length) are added from device memory, so the
+  // counter-based random policy keeps advancing.  nullptr outside graphs.
+  const uint64_t* step_base;
 };
 
 }  // namespace pcb

@@ -31,8 +31,10 @@ struct RolloutParams {
   const uint8_t* bank;
   const float* ratio_lut;
   double* stats;
-  const int32_t* actions;  // nullptr: the device random policy; else the actions of the one
-  int action_format;       // step to run (pcb_step): [N, 2|3] tuples or [N] flat indices
+  const int32_t* actions;  // nullptr: the device random policy; else the caller's actions,
+  int action_format;       // row t at actions + t * action_stride: [N, 2|3] tuples or [N] flat
+  size_t action_stride;    // (pcb_step: one row; pcb_steps_host: n_steps rows)
+  uint32_t res_stride;     // bytes between the two halves of the reward / done block
   int32_t* actions_log;  // nullptr or [n_steps, N, 2|3]
   double* reward_log;    // nullptr or [n_steps, N]
   uint8_t* done_log;     // nullptr or [n_steps, N]
@@ -276,21 +278,23 @@ rollout_small_kernel(const __grid_constant__ RolloutParams p) {
   for (int t = 0; t < p.n_steps; ++t) {
     const uint64_t step_no = p.step_no + (uint64_t)t;
     const uint32_t he = ((uint32_t)step_no & 1u) ? N + (uint32_t)env : (uint32_t)env;
+    const size_t hoff = ((uint32_t)step_no & 1u) ? (size_t)p.res_stride : 0;  // reward | done block
 
     int o = 0, x = 0, y = 0, ph = d.sq_n, pw = d.sq_n;
     bool valid;
     if (p.actions) {
+      const int32_t* acts = p.actions + (size_t)t * p.action_stride;
       // ---- given actions (pcb_step; FlatteningActionWrapper*: env_wrappers.py:80-98,
       // wrapper_square.py:54-69).  validate_action == mask bit, recomputed (square:155-173,
       // rect:434-457); actions outside the box are invalid ----
       if (p.action_format == 1) {
-        const int a = p.actions[env];
+        const int a = acts[env];
         if (a < 0) { o = -1; }
         else { o = a / HW; const int rem = a - o * HW; x = rem / W; y = rem - x * W; }
       } else if (kind == 0) {
-        x = p.actions[2 * env]; y = p.actions[2 * env + 1];
+        x = acts[2 * env]; y = acts[2 * env + 1];
       } else {
-        o = p.actions[3 * env]; x = p.actions[3 * env + 1]; y = p.actions[3 * env + 2];
+        o = acts[3 * env]; x = acts[3 * env + 1]; y = acts[3 * env + 2];
       }
       bool in_range = (unsigned)o < (unsigned)O && (unsigned)x < (unsigned)H && (unsigned)y < (unsigned)W;
       if (kind != 0) {
@@ -388,8 +392,8 @@ rollout_small_kernel(const __grid_constant__ RolloutParams p) {
     }
     const bool done = early || blocked;
     if (sl == 0 && live) {
-      p.base.done[he] = done ? 1 : 0;
-      p.base.reward[he] = reward;
+      p.base.done[hoff + (size_t)env] = done ? 1 : 0;
+      *reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(p.base.reward + env) + hoff) = reward;
       const size_t le = (size_t)t * N + (size_t)env;
       if (p.reward_log) p.reward_log[le] = reward;
       if (p.done_log) p.done_log[le] = done ? 1 : 0;

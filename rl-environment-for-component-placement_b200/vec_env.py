@@ -51,21 +51,25 @@ def _host_buffer(x, dtype, what):
 class HostStepper:
     """See PcbVecEnv.host_stepper."""
 
-    def __init__(self, env, actions, reward, done):
-        def addr(x, dtype, what):
-            return _host_buffer(x, dtype, what)
-
+    def __init__(self, env, actions, reward=None, done=None):
         n = env.num_envs
         if tuple(actions.shape[1:]) not in ((n,), (n, env.spec.action_width)):
             raise ValueError("actions must have shape [T, N] or [T, N, k]")
+        if reward is None and done is None:
+            # one packed pinned block [reward f64 x N | done u8 x N]: the library then needs a
+            # single device-to-host copy per step (pcb_step_host)
+            self.result = torch.empty(n * 9, dtype=torch.uint8, pin_memory=True)
+            reward = self.result[: n * 8].view(torch.float64)
+            done = self.result[n * 8:]
         if tuple(reward.shape) != (n,) or tuple(done.shape) != (n,):
             raise ValueError("reward and done must have shape [N]")
+        self.reward, self.done = reward, done
         self._keep = (actions, reward, done)  # the buffers must outlive the stepper
         self._env, self._fn, self._h = env, env.lib.pcb_step_host, env._h
         self._fmt = 1 if len(actions.shape) == 2 else 0
         row = n * (1 if self._fmt else env.spec.action_width) * 4
-        self._a0, self._row = addr(actions, "int32", "actions"), row
-        self._r, self._d = addr(reward, "float64", "reward"), addr(done, "uint8", "done")
+        self._a0, self._row = _host_buffer(actions, "int32", "actions"), row
+        self._r, self._d = _host_buffer(reward, "float64", "reward"), _host_buffer(done, "uint8", "done")
         self._steps = int(actions.shape[0])
         self._stream = torch.cuda.current_stream(env.device).cuda_stream
 
@@ -283,6 +287,15 @@ class PcbVecEnv:
         """rollout_random: run the reward kernel of step t alongside the step kernel of t+1."""
         self._check(self.lib.pcb_set_reward_overlap(self._h, 1 if on else 0))
 
+    def graph_rollout(self, on):
+        """rollout_random of the per-step kinds as CUDA-graph replays (default on) or plain
+        launches; same results."""
+        self._check(self.lib.pcb_set_graph_rollout(self._h, 1 if on else 0))
+
+    @property
+    def graph_replays(self):
+        return int(self.lib.pcb_graph_replays(self._h))
+
     def fused_rollout(self, on):
         """Pin-less kinds: rollout_random as one multi-step launch (default) or per-step
         launches.  Returns True when the fused kernel will be used."""
@@ -320,13 +333,32 @@ class PcbVecEnv:
         d = _host_buffer(done_np, "uint8", "done")
         self._check(self.lib.pcb_step_host(self._h, a, fmt, r, d, self._stream()))
 
-    def host_stepper(self, actions, reward, done):
+    def host_stepper(self, actions, reward=None, done=None):
         """Pre-binds host buffers for repeated pcb_step_host calls: ``actions`` [T, N] (flat) or
         [T, N, k] int32, ``reward`` [N] float64, ``done`` [N] uint8 (numpy arrays or CPU
         tensors, C-contiguous, ideally pinned).  The returned callable ``f(t)`` steps with row t
         of ``actions``; per call it costs one ctypes call (~2 us of host time instead of ~8: the
-        host time between two synchronous steps is time the GPU idles)."""
+        host time between two synchronous steps is time the GPU idles).  Without ``reward`` /
+        ``done`` the stepper owns one packed pinned result block (``f.reward``, ``f.done`` are
+        views of it) and every step needs a single device-to-host copy."""
         return HostStepper(self, actions, reward, done)
+
+    def steps_host(self, actions, reward, done):
+        """T steps from host buffers in one call (pcb_steps_host): ``actions`` int32 [T, N]
+        (flat) or [T, N, k]; ``reward`` float64 [T, N] and ``done`` uint8 [T, N] receive every
+        step's results.  Each step's action row is copied up and its results are copied down
+        while neighbouring steps run; the call returns when everything has arrived.  Same
+        results as T calls of ``step_host``."""
+        n, T = self.num_envs, int(actions.shape[0])
+        if tuple(actions.shape[1:]) not in ((n,), (n, self.spec.action_width)):
+            raise ValueError("actions must have shape [T, N] or [T, N, k]")
+        if tuple(reward.shape) != (T, n) or tuple(done.shape) != (T, n):
+            raise ValueError("reward and done must have shape [T, N]")
+        fmt = 1 if len(actions.shape) == 2 else 0
+        self._check(self.lib.pcb_steps_host(
+            self._h, _host_buffer(actions, "int32", "actions"), T, fmt,
+            _host_buffer(reward, "float64", "reward"), _host_buffer(done, "uint8", "done"),
+            self._stream()))
 
     # -- views ---------------------------------------------------------------
     @property

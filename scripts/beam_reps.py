@@ -13,7 +13,7 @@ import __graft_entry__ as ge  # noqa: E402
 ge.build()
 import pcbgpu  # noqa: E402
 from bench import stagger  # noqa: E402
-from ref_harness import CONFIGS  # noqa: E402
+from pcbgpu.configs import CONFIGS  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "C_both"
 N, K = 65536, 128

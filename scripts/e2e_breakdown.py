@@ -13,7 +13,7 @@ import __graft_entry__ as ge  # noqa: E402
 
 ge.build()
 import pcbgpu  # noqa: E402
-from ref_harness import CONFIGS  # noqa: E402
+from pcbgpu.configs import CONFIGS  # noqa: E402
 
 if os.environ.get("USE_STREAM"):
     torch.cuda.set_stream(torch.cuda.Stream())

@@ -454,3 +454,121 @@ def test_specialised_library_for_a_pin_less_config():
     assert np.array_equal(env.state_dict()["state"], ref.state_dict()["state"])
     env.close(); ref.close()
     run_parity("S_rect", range(24), extra_steps=2, p_invalid=0.2, specialize=True)
+
+
+@pytest.mark.parametrize("name", ["C", "C_both", "D", "E", "B", "A", "S_rect", "S_pin", "S_wide_rect"])
+@pytest.mark.parametrize("tuples", [False, True])
+def test_steps_host_equals_repeated_step_host(name, tuples):
+    """pcb_steps_host (T rows in one call: copies overlapped with neighbouring steps, pin-less
+    kinds in one launch) == T x pcb_step_host, for every result row, the observations of every
+    step (ring), the result tensors and the episode statistics."""
+    n, T = 77, 19  # more than two upload chunks, odd sizes
+    a = make(name, n, seed=6, obs_ring=T + 1)
+    b = make(name, n, seed=6, obs_ring=T + 1)
+    c = make(name, n, seed=6)
+    w = a.spec.action_width
+    log = torch.zeros((T, n, w), dtype=torch.int32, device="cuda")
+    c.reset(); c.rollout_random(T, seed=3, actions_log=log); c.close()
+    log[T // 2, ::5] = -1          # some invalid actions
+    H, W = a.spec.height, a.spec.width
+    if tuples:
+        acts = log.cpu().pin_memory()
+    else:
+        flat = (log[..., 0] * H + log[..., 1]) * W + log[..., 2] if w == 3 else log[..., 0] * W + log[..., 1]
+        flat[T // 2, ::5] = -7
+        acts = flat.int().cpu().pin_memory()
+    a.reset(); b.reset()
+    R = torch.zeros((T, n), dtype=torch.float64).pin_memory()
+    D = torch.zeros((T, n), dtype=torch.uint8).pin_memory()
+    a.steps_host(acts, R, D)
+    f = b.host_stepper(acts)        # packed result block: one D2H copy per step
+    for t in range(T):
+        f(t)
+        assert np.array_equal(f.reward.numpy(), R[t].numpy()), (name, t)
+        assert np.array_equal(f.done.numpy(), D[t].numpy()), (name, t)
+    torch.cuda.synchronize()
+    for k in a.obs_ring_tensors:
+        assert torch.equal(a.obs_ring_tensors[k], b.obs_ring_tensors[k]), (name, k)
+    ra, rb = a.results(), b.results()
+    for k in ra:
+        assert torch.equal(ra[k], rb[k]), (name, k)
+    sa, sb = a.episode_stats(), b.episode_stats()
+    for k in sa:  # the sums are float64 atomics: the order of the additions is not fixed
+        assert sa[k] == sb[k] if k in ("episodes", "steps", "sum_length") else np.isclose(sa[k], sb[k], rtol=1e-12), k
+    assert int(D.sum()) > 0
+    # a second call continues the same trajectories (staging reused, parity of the halves)
+    a.steps_host(acts[:3], R[:3], D[:3])
+    for t in range(3):
+        f(t)
+        assert np.array_equal(f.reward.numpy(), R[t].numpy()) and np.array_equal(f.done.numpy(), D[t].numpy())
+    a.close(); b.close()
+
+
+def test_steps_host_without_reward_overlap_and_argument_checks():
+    n, T = 64, 5
+    a, b = make("C", n, seed=1), make("C", n, seed=1)
+    a.reward_overlap(False)
+    acts = torch.zeros((T, n), dtype=torch.int32).pin_memory()
+    acts[:] = torch.arange(n, dtype=torch.int32) % 700
+    Ra, Da = torch.zeros((T, n), dtype=torch.float64), torch.zeros((T, n), dtype=torch.uint8)
+    Rb, Db = torch.zeros((T, n), dtype=torch.float64), torch.zeros((T, n), dtype=torch.uint8)
+    a.reset(); b.reset()
+    a.steps_host(acts, Ra, Da)      # pageable host memory works too
+    b.steps_host(acts, Rb, Db)
+    assert torch.equal(Ra, Rb) and torch.equal(Da, Db)
+    with pytest.raises(ValueError):
+        a.steps_host(acts, Ra[:2], Da)
+    with pytest.raises(ValueError):
+        a.steps_host(acts.long(), Ra, Da)
+    with pytest.raises(ValueError):
+        a.steps_host(acts, Ra.float(), Da)
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("name,ring", [("C", 4), ("C_both", 2), ("D", 5), ("S_pin", 3), ("S_wide_rect", 4)])
+def test_graph_rollout_equals_plain_launches(name, ring):
+    """pcb_rollout_random of the per-step kinds replays a CUDA graph of L steps; the result must
+    be the plain per-step launches' bit for bit: every observation slice, the state records,
+    the results of the last step, the episode statistics -- across several calls, a partial
+    reset in between and a bank upload (which invalidates the captured graph)."""
+    n = 200
+    a = make(name, n, seed=9, obs_ring=ring, bank_size=3 * n)
+    b = make(name, n, seed=9, obs_ring=ring, bank_size=3 * n)
+    b.graph_rollout(False)
+    a.reset(); b.reset()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(torch.cuda.Stream()):  # the default stream cannot be captured
+        _graph_rollout_body(name, n, a, b)
+    a.close(); b.close()
+
+
+def _graph_rollout_body(name, n, a, b):
+    def same(tag):
+        torch.cuda.synchronize()
+        for k in a.obs_ring_tensors:
+            assert torch.equal(a.obs_ring_tensors[k], b.obs_ring_tensors[k]), (name, tag, k)
+        assert np.array_equal(a.state_dict()["state"], b.state_dict()["state"]), (name, tag)
+        ra, rb = a.results(), b.results()
+        for k in ("reward", "done"):
+            assert torch.equal(ra[k], rb[k]), (name, tag, k)
+        sa, sb = a.episode_stats(), b.episode_stats()
+        assert sa["episodes"] == sb["episodes"] and sa["sum_length"] == sb["sum_length"], (name, tag)
+        assert np.isclose(sa["sum_return"], sb["sum_return"], rtol=1e-12), (name, tag)
+
+    for e in (a, b):
+        e.rollout_random(71, seed=5)      # several replays + a remainder
+    same("first")
+    assert a.graph_replays >= 2 and b.graph_replays == 0
+    r0 = a.graph_replays
+    for e in (a, b):
+        e.rollout_random(40, seed=5)      # the captured graph is reused when the phase allows
+        e.reset(mask=(torch.arange(n, device="cuda") % 7 == 0))
+        e.rollout_random(33, seed=6)      # another seed: recaptured
+    same("second")
+    assert a.graph_replays > r0
+    for e in (a, b):
+        e.generate_instances(2 * n, seed=123)   # new bank: the graph carried the old pointer
+        e.rollout_random(50, seed=6)
+        e.step(e.sample_random_actions(seed=1))  # plain step in between
+        e.rollout_random(37, seed=6)
+    same("third")
