@@ -100,7 +100,7 @@ struct pcb_env {
   bool use_graph;
   cudaGraphExec_t graph;
   int graph_len, graph_slice;
-  uint64_t graph_next_step, graph_seed;  // replay is valid when the handle is exactly here
+  uint64_t graph_step0, graph_seed;      // step number and seed at capture
   cudaStream_t graph_stream;
   bool graph_overlap;
   uint64_t* d_step_base;
@@ -575,7 +575,7 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
   e->ratio_lut = nullptr; e->d_actions = nullptr; e->d_actions2 = nullptr;
   e->res_stride = 0; e->hs_actions = nullptr; e->hs_reward = nullptr; e->hs_done = nullptr;
   e->hs_steps = 0; e->copy = nullptr; e->ev_host = nullptr;
-  e->use_graph = true; e->graph = nullptr; e->graph_len = 0; e->graph_slice = 0; e->graph_next_step = 0;
+  e->use_graph = true; e->graph = nullptr; e->graph_len = 0; e->graph_slice = 0; e->graph_step0 = 0;
   e->graph_seed = 0; e->graph_stream = nullptr; e->graph_overlap = false; e->d_step_base = nullptr;
   e->graph_launches = 0; e->graph_replays = 0;
   memset(&e->base, 0, sizeof e->base);
@@ -1120,79 +1120,101 @@ static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
 // pcb_rollout_random of the per-step kinds as CUDA-graph replays.  One graph = L consecutive
 // steps with L a multiple of the observation ring, of the 4 job counters and of 2 (result
 // halves, action ping-pong): after L steps every pointer a launch carries is the same
-// again, so the captured graph can be replayed as is.  The one thing that must keep moving
-// -- the step counter of the random policy -- is read from device memory (Params::step_base)
-// and advanced by the last node.  *done_steps = steps executed here (a multiple of L); the
-// caller runs the remainder with plain launches.  Actions of the first step: d_actions.
-static int rollout_graphed(pcb_env_t* e, uint64_t seed, int n_steps, cudaStream_t st, int* done_steps) {
-  *done_steps = 0;
-  if (!e->use_graph || e->timing || e->fused) return 0;
-  // the default streams cannot be captured
-  if (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) return 0;
+// again, so the captured graph can be replayed whenever the handle is in the phase it was
+// captured in (same ring slice, same step number modulo 4).  The one thing that must keep
+// moving -- the step counter of the random policy -- is read from device memory
+// (Params::step_base = steps since capture), set before a run of replays and advanced by the
+// last node of the graph.
+static int graph_length(const pcb_env_t* e) {
   const int base = e->ring * 4 / gcd_i(e->ring, 4);  // lcm(ring, 4)
-  if (base > 128 || n_steps < base) return 0;
-  const int L = base * std::max(1, 16 / base);       // at least ~16 steps per launch
-  if (n_steps < L) return 0;
+  if (base > 128) return 0;
+  return base * std::max(1, 16 / base);              // at least ~16 steps per launch
+}
+
+static bool graph_allowed(pcb_env_t* e, cudaStream_t st) {
+  if (!e->use_graph || e->timing || e->fused) return false;
+  // the default streams cannot be captured
+  if (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) return false;
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
     cudaGetLastError();
-    return 0;  // the caller is capturing this stream itself
+    return false;  // the caller is capturing this stream itself
   }
-  const bool overlap = e->overlap && e->d.kind >= 2;
-  const bool reuse = e->graph && e->graph_len == L && e->graph_slice == e->slice &&
-                     e->graph_next_step == e->step_no && e->graph_seed == seed &&
-                     e->graph_stream == st && e->graph_overlap == overlap;
-  if (!reuse) {
-    if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
-    int rc = join_rewards(e, st);  // no event of an earlier, un-captured launch may be waited on
-    if (rc) return rc;
-    CU(cudaMemsetAsync(e->d_step_base, 0, sizeof(uint64_t), st));
-    const uint64_t step0 = e->step_no;
-    const int slice0 = e->slice;
-    const int64_t launches0 = e->launches;
-    CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-    int32_t* cur = e->d_actions;
-    for (int t = 0; t < L && rc == 0; ++t) {
-      int32_t* nxt = cur == e->d_actions ? e->d_actions2 : e->d_actions;
-      rc = step_impl(e, cur, PCB_ACTION_TUPLE, seed, nxt, st, overlap, nullptr, nullptr, e->d_step_base);
-      cur = nxt;
-    }
-    if (rc == 0) rc = join_rewards(e, st);
-    if (rc == 0) {
-      advance_step_base_kernel<<<1, 1, 0, st>>>(e->d_step_base, (uint64_t)L);
-      if (cudaGetLastError() != cudaSuccess) rc = fail(PCB_ERR_CUDA, "advance_step_base_kernel launch failed");
-    }
-    cudaGraph_t g = nullptr;
-    cudaError_t ce = cudaStreamEndCapture(st, &g);
-    // capture only records: put the host-side bookkeeping back to where the handle really is
-    e->step_no = step0; e->slice = slice0;
-    e->graph_launches = e->launches - launches0 + 1;
-    e->launches = launches0;
-    e->rew_pending[0] = e->rew_pending[1] = false;
-    if (rc || ce != cudaSuccess || !g) {
-      if (g) cudaGraphDestroy(g);
-      cudaGetLastError();
-      e->use_graph = false;  // this configuration cannot be captured: plain launches from now on
-      return rc ? rc : 0;
-    }
+  return true;
+}
+
+// plain steps needed before the captured graph fits the handle's phase (0 = now), -1 = never
+static int graph_align_distance(const pcb_env_t* e, int L) {
+  for (int dlt = 0; dlt < L; ++dlt) {
+    const bool slice_ok = (e->slice + dlt) % e->ring == e->graph_slice;
+    const bool step_ok = ((e->step_no + (uint64_t)dlt - e->graph_step0) & 3) == 0 &&
+                         e->step_no + (uint64_t)dlt >= e->graph_step0;
+    if (slice_ok && step_ok) return dlt;
+  }
+  return -1;
+}
+
+// captures L steps starting at the handle's current phase (actions of the first step in d_actions)
+static int graph_capture(pcb_env_t* e, uint64_t seed, int L, cudaStream_t st, bool overlap) {
+  if (e->graph) { cudaGraphExecDestroy(e->graph); e->graph = nullptr; }
+  int rc = join_rewards(e, st);  // no event of an earlier, un-captured launch may be waited on
+  if (rc) return rc;
+  const uint64_t step0 = e->step_no;
+  const int slice0 = e->slice;
+  const int64_t launches0 = e->launches;
+  CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+  int32_t* cur = e->d_actions;
+  for (int t = 0; t < L && rc == 0; ++t) {
+    int32_t* nxt = cur == e->d_actions ? e->d_actions2 : e->d_actions;
+    rc = step_impl(e, cur, PCB_ACTION_TUPLE, seed, nxt, st, overlap, nullptr, nullptr, e->d_step_base);
+    cur = nxt;
+  }
+  if (rc == 0) rc = join_rewards(e, st);
+  if (rc == 0) {
+    advance_step_base_kernel<<<1, 1, 0, st>>>(e->d_step_base, (uint64_t)L);
+    if (cudaGetLastError() != cudaSuccess) rc = fail(PCB_ERR_CUDA, "advance_step_base_kernel launch failed");
+  }
+  cudaGraph_t g = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(st, &g);
+  // capture only records: put the host-side bookkeeping back to where the handle really is
+  e->step_no = step0; e->slice = slice0;
+  e->graph_launches = e->launches - launches0;
+  e->launches = launches0;
+  e->rew_pending[0] = e->rew_pending[1] = false;
+  if (rc == 0 && (ce != cudaSuccess || !g)) rc = fail(PCB_ERR_CUDA, "graph capture: %s", cudaGetErrorString(ce));
+  if (rc == 0) {
     ce = cudaGraphInstantiate(&e->graph, g, 0);
-    cudaGraphDestroy(g);
-    if (ce != cudaSuccess) {
-      e->graph = nullptr; e->use_graph = false;
-      cudaGetLastError();
-      return 0;
-    }
-    e->graph_len = L; e->graph_slice = slice0; e->graph_seed = seed; e->graph_stream = st;
-    e->graph_overlap = overlap;
+    if (ce != cudaSuccess) { e->graph = nullptr; rc = fail(PCB_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ce)); }
   }
-  while (n_steps - *done_steps >= L) {
+  if (g) cudaGraphDestroy(g);
+  if (rc) {
+    cudaGetLastError();
+    e->use_graph = false;  // this configuration cannot be captured: plain launches from now on
+    return rc;
+  }
+  e->graph_len = L; e->graph_slice = slice0; e->graph_step0 = step0; e->graph_seed = seed;
+  e->graph_stream = st; e->graph_overlap = overlap;
+  return 0;
+}
+
+// replays while at least L steps remain; the handle must be in the captured phase
+static int graph_replay(pcb_env_t* e, int* remaining, cudaStream_t st) {
+  const int L = e->graph_len;
+  if (*remaining < L) return 0;
+  // the graph knows nothing of reward kernels launched outside it: a plain step just before
+  // may still have one in flight on the side stream, reading the job buffer the graph's
+  // second step writes
+  int rc = join_rewards(e, st);
+  if (rc) return rc;
+  set_step_base_kernel<<<1, 1, 0, st>>>(e->d_step_base, e->step_no - e->graph_step0);
+  CU(cudaGetLastError());
+  while (*remaining >= L) {
     CU(cudaGraphLaunch(e->graph, st));
     e->step_no += (uint64_t)L;  // L is a multiple of the ring: the slice index is unchanged
     e->launches += e->graph_launches;
     e->graph_replays += 1;
-    *done_steps += L;
+    *remaining -= L;
   }
-  e->graph_next_step = e->step_no;
   return 0;
 }
 
@@ -1209,33 +1231,60 @@ int pcb_rollout_random_logged(pcb_env_t* e, uint64_t seed, int n_steps, int32_t*
     return rollout_fused(e, seed, n_steps, d_actions_log, d_reward_log, d_done_log, (cudaStream_t)stream,
                          nullptr, 0);
   const size_t N = (size_t)e->n_envs, per = N * (e->d.kind == 0 ? 2 : 3);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int total_steps = n_steps;
+  // CUDA-graph plan: `dlt` plain steps walk the handle into the phase the graph was captured
+  // in (or a graph is captured right here, dlt = 0), then replays, then the remainder
+  const int L = graph_length(e);
+  const bool overlap = e->overlap && e->d.kind >= 2;
+  bool graphed = !d_actions_log && !d_reward_log && !d_done_log && L > 0 && n_steps >= L && graph_allowed(e, st);
+  bool capture = false;
+  int dlt = 0;
+  if (graphed) {
+    const bool usable = e->graph && e->graph_len == L && e->graph_seed == seed &&
+                        e->graph_stream == st && e->graph_overlap == overlap;
+    dlt = usable ? graph_align_distance(e, L) : -1;
+    if (dlt < 0) { capture = true; dlt = 0; }
+    if (n_steps - dlt < L) graphed = false;
+  }
   // the first action comes from the stand-alone sampler; every step kernel then also
-  // draws the action of the following step (same counter as the sampler would use)
-  int32_t* cur = d_actions_log ? d_actions_log : e->d_actions;
+  // draws the action of the following step (same counter as the sampler would use).  The two
+  // action buffers ping-pong; a replay expects its first actions in d_actions.
+  int32_t* cur = d_actions_log ? d_actions_log : ((graphed && (dlt & 1)) ? e->d_actions2 : e->d_actions);
   rc = pcb_sample_random_actions(e, seed, cur, stream);
   if (rc) return rc;
-  if (!d_actions_log && !d_reward_log && !d_done_log) {
-    int done_steps = 0;
-    rc = rollout_graphed(e, seed, n_steps, (cudaStream_t)stream, &done_steps);
-    if (rc) return rc;
-    if (done_steps == n_steps) return 0;
-    n_steps -= done_steps;  // the rest (less than one graph) with per-step launches
-    // a graph ends with the actions of its successor in d_actions, as the sampler left them
+  // plain per-step launches; `cur` holds the actions of the next step throughout
+  auto plain = [&](int count, bool last_of_call) -> int {
+    for (int t = 0; t < count; ++t) {
+      const int done = total_steps - n_steps;
+      int32_t* nxt = nullptr;
+      if (!(last_of_call && t + 1 == count))
+        nxt = d_actions_log ? d_actions_log + (size_t)(done + 1) * per
+                            : (cur == e->d_actions ? e->d_actions2 : e->d_actions);
+      int rc2 = step_impl(e, cur, PCB_ACTION_TUPLE, seed, nxt, stream, e->overlap,
+                          d_reward_log ? d_reward_log + (size_t)done * N : nullptr,
+                          d_done_log ? d_done_log + (size_t)done * N : nullptr);
+      if (rc2) return rc2;
+      cur = nxt;
+      n_steps -= 1;
+    }
+    return 0;
+  };
+  if (graphed) {
+    if (capture && graph_capture(e, seed, L, st, overlap) != 0) graphed = false;  // plain launches then
   }
-  for (int t = 0; t < n_steps; ++t) {
-    int32_t* nxt = nullptr;
-    if (t + 1 < n_steps)
-      nxt = d_actions_log ? d_actions_log + (size_t)(t + 1) * per
-                          : (cur == e->d_actions ? e->d_actions2 : e->d_actions);
-    rc = step_impl(e, cur, PCB_ACTION_TUPLE, seed, nxt, stream, e->overlap,
-                   d_reward_log ? d_reward_log + (size_t)t * N : nullptr,
-                   d_done_log ? d_done_log + (size_t)t * N : nullptr);
+  if (graphed) {
+    rc = plain(dlt, false);
     if (rc) return rc;
-    cur = nxt;
+    if (cur != e->d_actions) return fail(PCB_ERR_STATE, "internal: action ping-pong out of phase");
+    rc = graph_replay(e, &n_steps, st);
+    if (rc) return rc;
   }
+  rc = plain(n_steps, true);
+  if (rc) return rc;
   rc = join_rewards(e, (cudaStream_t)stream);
   if (rc) return rc;
-  return restore_result_halves(e, n_steps, d_reward_log, d_done_log, (cudaStream_t)stream);
+  return restore_result_halves(e, total_steps, d_reward_log, d_done_log, (cudaStream_t)stream);
 }
 
 // the result tensors ([2] halves by step parity) describe the last two steps: copy them back

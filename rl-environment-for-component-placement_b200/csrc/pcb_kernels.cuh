@@ -675,6 +675,7 @@ __device__ __forceinline__ uint64_t policy_step(const Params& p) {
 
 // last node of a captured rollout graph: the next replay is `n` steps further on
 __global__ void advance_step_base_kernel(uint64_t* step_base, uint64_t n) { *step_base += n; }
+__global__ void set_step_base_kernel(uint64_t* step_base, uint64_t v) { *step_base = v; }
 
 // ---------------------------------------------------------------------------
 // observation write-out (everything the reference copies into the obs dict:
@@ -1233,6 +1234,9 @@ __device__ __forceinline__ void finish_episode(const S& sh, const Params& p, Env
 #ifndef PCB_OPT_PERSIST
 #define PCB_OPT_PERSIST 0
 #endif
+#ifndef PCB_OPT_PREFETCH
+#define PCB_OPT_PREFETCH 0   // > 0: L2-prefetch the state of the CTA this many blocks ahead
+#endif
 // the action of one env as (o, x, y): tuple or flat (FlatteningActionWrapper*:
 // env_wrappers.py:80-98, wrapper_square.py:54-69)
 template <typename S>
@@ -1393,6 +1397,17 @@ step_kernel(const Params p) {
   const bool live = env < p.n_envs;
   // issue every global load of this warp before anything waits: table, state, action
   const uint4 lut_part = expand_lut_fetch();
+#if PCB_OPT_PREFETCH
+  {
+    // The state records come back from DRAM every step (they do not survive ~500 MB of
+    // observation stores in L2) and the first use of the loaded record is the top stall of
+    // this kernel.  CTAs start roughly in blockIdx order, so the CTA PCB_OPT_PREFETCH blocks
+    // further on starts about one CTA lifetime later: pull its records into L2 now.
+    const int penv = env + PCB_OPT_PREFETCH * kWarpsPerCta;
+    if (penv < p.n_envs && lane * 128 < sh.st_stride())
+      asm volatile("prefetch.global.L2 [%0];" :: "l"(p.state + (size_t)penv * sh.st_stride() + lane * 128));
+  }
+#endif
   uint4 st0 = make_uint4(0, 0, 0, 0);
   if (lane < n16) st0 = ld_state(reinterpret_cast<const uint4*>(p.state + (size_t)(live ? env : 0) * sh.st_stride()) + lane);
   int o = 0, x = 0, y = 0;
