@@ -21,6 +21,7 @@
 #include "pcb_gen_device.cuh"
 #include "pcb_kernels.cuh"
 #include "pcb_small.cuh"
+#include "pcb_pin_small.cuh"
 
 using namespace pcb;
 
@@ -118,6 +119,13 @@ struct pcb_env {
   bool overlap;          // pcb_rollout_random overlaps the reward kernel with the next step
   int sms;               // multiprocessors of the device
   bool fused;            // pcb_rollout_random uses rollout_small_kernel (pin-less kinds, H, W <= 32)
+  // pin env, centroid reward, H, W <= 32: rollout_pin_kernel (pcb_pin_small.cuh) -- many steps
+  // per launch, 32/LPE envs per warp, terminal rewards from a job list afterwards
+  bool fused_pin, fused_pin_ok;
+  size_t pin_smem;       // dynamic shared memory per CTA (4 warps)
+  uint8_t* pin_jobs;     // job list of one launch, pin_job_steps * N records
+  uint32_t* pin_job_total;
+  int pin_job_steps;     // steps per launch the list is sized for
   size_t small_smem;     // its dynamic shared memory per CTA
   double fused_ms;       // timing (pcb_enable_kernel_timing): device time, launches, env-steps
   int64_t fused_launches, fused_steps;
@@ -377,6 +385,37 @@ int small_dispatch(pcb_env* e, bool configure, cudaStream_t st, const RolloutPar
   return small_launch_lpe<DynShape>(lpe, configure, sm, grid, block, st, p);
 }
 
+// rollout_pin_kernel: instantiations and dispatch (LPE follows from H)
+template <typename S, int LPE>
+int pin_launch(bool configure, size_t sm, dim3 grid, dim3 block, cudaStream_t st, const PinRolloutParams& p) {
+  if (configure) return set_smem(rollout_pin_kernel<LPE, S>, sm);
+  rollout_pin_kernel<LPE, S><<<grid, block, sm, st>>>(p);
+  return 0;
+}
+
+int pin_dispatch(pcb_env* e, bool configure, cudaStream_t st, const PinRolloutParams& p) {
+  const int lpe = small_lanes_per_env(e->d.H), G = 32 / lpe;
+  const int warps = (e->n_envs + G - 1) / G;
+  const int wpc = warps <= e->sms * 32 ? 1 : kWarpsPerCta;
+  dim3 grid((warps + wpc - 1) / wpc), block(wpc * 32);
+  const PinSmem L = pin_smem_layout(e->d.C, e->d.L.P, e->d.max_pins, e->d.H * e->d.W);
+  const size_t sm = configure ? e->pin_smem : (size_t)kLutBytes + (size_t)L.total * wpc * G;
+  switch (e->shape_id) {
+    case 2: return pin_launch<ShapeC, 32>(configure, sm, grid, block, st, p);
+    case 5: return pin_launch<ShapeRefPin, 16>(configure, sm, grid, block, st, p);
+#ifdef PCB_USER_SHAPE
+    case 100:
+      if constexpr (kUserDims[0] == 2 && !kUserWide)
+        return pin_launch<ShapeUser, small_lanes_per_env(kUserDims[1])>(configure, sm, grid, block, st, p);
+      break;
+#endif
+    default: break;
+  }
+  if (lpe == 8) return pin_launch<DynShape, 8>(configure, sm, grid, block, st, p);
+  if (lpe == 16) return pin_launch<DynShape, 16>(configure, sm, grid, block, st, p);
+  return pin_launch<DynShape, 32>(configure, sm, grid, block, st, p);
+}
+
 constexpr size_t kGuardBytes = 4096;
 constexpr int kGuardByte = 0xA5;
 
@@ -613,6 +652,8 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
       else TRY((set_smem_shape<1, uint32_t, DynShape>(e->smem_bytes)));
   }
   e->fused = d.kind <= 1 && !e->wide;
+  e->fused_pin = false; e->fused_pin_ok = false; e->pin_smem = 0; e->pin_jobs = nullptr;
+  e->pin_job_total = nullptr; e->pin_job_steps = 0;
   e->sms = 148;
   cudaDeviceGetAttribute(&e->sms, cudaDevAttrMultiProcessorCount, device);
   e->small_smem = 0; e->fused_ms = 0.0; e->fused_launches = 0; e->fused_steps = 0;
@@ -623,6 +664,25 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
     memset(&none, 0, sizeof none);
     TRY(small_dispatch(e, true, nullptr, none));
   }
+  if (d.kind == 2 && !e->wide && d.reward_type == PCB_REWARD_CENTROID && cfg->reserved0 != 1) {
+    // Small boards pack several envs into a warp; a small batch of any board is launch- and
+    // latency-bound with one launch per step.  A large batch of a 32-row board keeps the
+    // per-step kernels (one warp per env either way, and the reward kernel overlaps the next
+    // step there instead of running after the rollout).
+    const int lpe = small_lanes_per_env(d.H);
+    int max_envs = 32768;
+    if (const char* f = getenv("PCB_PIN_FUSED_MAX_ENVS")) max_envs = atoi(f);
+    e->fused_pin_ok = true;
+    e->fused_pin = lpe < 32 || num_envs <= max_envs;
+    const PinSmem L = pin_smem_layout(d.C, d.L.P, d.max_pins, d.H * d.W);
+    e->pin_smem = (size_t)kLutBytes + (size_t)L.total * kWarpsPerCta * (32 / lpe);
+    if (e->pin_smem > 200 * 1024) { e->fused_pin_ok = false; e->fused_pin = false; }
+    if (e->fused_pin_ok) {
+      PinRolloutParams none;
+      memset(&none, 0, sizeof none);
+      TRY(pin_dispatch(e, true, nullptr, none));
+    }
+  }
   e->jobs = nullptr; e->job_count = nullptr; e->reward_smem = 0; e->reward_grid = 1; e->reward_grid_side = 1;
   e->side = nullptr; e->rew_pending[0] = e->rew_pending[1] = false; e->overlap = PCB_OVERLAP_REWARD != 0;
   for (int i = 0; i < 2; ++i) { e->ev_step[i] = nullptr; e->ev_rew[i] = nullptr; }
@@ -630,6 +690,7 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
     e->reward_smem = (size_t)((route_scratch_bytes(d.max_pins, d.K) + 15) & ~15) * kWarpsPerCta;
     TRY(set_smem(reward_kernel<false>, e->reward_smem));
     TRY(set_smem(reward_kernel<true>, e->reward_smem));
+    TRY(set_smem(reward_list_kernel, e->reward_smem));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     int want = (num_envs + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -739,6 +800,7 @@ int pcb_destroy(pcb_env_t* e) {
   if (e->copy) cudaStreamDestroy(e->copy);
   if (e->ev_host) cudaEventDestroy(e->ev_host);
   for (cudaEvent_t ev : e->hs_events) cudaEventDestroy(ev);
+  if (e->pin_jobs) cudaFree(e->pin_jobs);
   if (e->hs_actions) cudaFree(e->hs_actions);
   if (e->hs_reward) cudaFree(e->hs_reward);
   if (e->hs_done) cudaFree(e->hs_done);
@@ -1115,6 +1177,83 @@ static int rollout_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_ac
   return 0;
 }
 
+// the pin env: n_steps in launches of up to pin_job_steps steps of rollout_pin_kernel, each
+// followed by reward_list_kernel over the routing jobs it left.  d_actions != nullptr: the
+// caller's action rows instead of the random policy (pcb_steps_host).
+static int rollout_pin_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_actions_log,
+                             double* d_reward_log, uint8_t* d_done_log, cudaStream_t st,
+                             const int32_t* d_actions, int action_format) {
+  CU(cudaSetDevice(e->device));
+  const size_t N = (size_t)e->n_envs;
+  const size_t jstride = (size_t)job_stride(e->d.max_pins, e->d.K);
+  // the list must hold a job per env and step (every env can finish an episode every step
+  // when its instance has one component): at most 256 MB, at most 64 steps per launch
+  const int want = (int)std::max<size_t>(1, std::min<size_t>(64, (256u << 20) / (N * jstride)));
+  if (!e->pin_jobs || e->pin_job_steps < std::min(want, n_steps)) {
+    CU(cudaStreamSynchronize(st));
+    if (e->pin_jobs) { cudaFree(e->pin_jobs); e->pin_jobs = nullptr; }
+    void* q = nullptr;
+    cudaError_t err = cudaMalloc(&q, (size_t)want * N * jstride + 16);
+    if (err != cudaSuccess)
+      return fail(err == cudaErrorMemoryAllocation ? PCB_ERR_NOMEM : PCB_ERR_CUDA, "job list: %s", cudaGetErrorString(err));
+    e->pin_jobs = (uint8_t*)q;
+    e->pin_job_total = reinterpret_cast<uint32_t*>(e->pin_jobs + (size_t)want * N * jstride);
+    e->pin_job_steps = want;
+  }
+  const size_t per = N * (action_format == PCB_ACTION_FLAT ? 1 : 3);
+  cudaEvent_t a = nullptr, b = nullptr;
+  if (e->timing) {
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    CU(cudaEventRecord(a, st));
+  }
+  for (int t0 = 0; t0 < n_steps; t0 += e->pin_job_steps) {
+    const int nt = std::min(e->pin_job_steps, n_steps - t0);
+    CU(cudaMemsetAsync(e->pin_job_total, 0, sizeof(uint32_t), st));
+    PinRolloutParams p;
+    memset(&p, 0, sizeof p);
+    p.d = e->d; p.base = e->base;
+    p.state = e->state; p.bank = e->bank; p.ratio_lut = e->ratio_lut; p.stats = e->stats;
+    p.actions = d_actions ? d_actions + (size_t)t0 * per : nullptr;
+    p.action_format = action_format; p.action_stride = d_actions ? per : 0;
+    p.res_stride = (uint32_t)e->res_stride;
+    p.actions_log = d_actions_log ? d_actions_log + (size_t)t0 * N * 3 : nullptr;
+    p.reward_log = d_reward_log ? d_reward_log + (size_t)t0 * N : nullptr;
+    p.done_log = d_done_log ? d_done_log + (size_t)t0 * N : nullptr;
+    p.seed = seed; p.step_no = e->step_no; p.bank_count = e->bank_count;
+    p.slot_step = e->bank_count ? (uint32_t)e->n_envs % e->bank_count : (uint32_t)e->n_envs;
+    p.n_envs = e->n_envs; p.n_steps = nt; p.ring = e->ring; p.slice0 = e->slice;
+    p.jobs = e->pin_jobs; p.job_total = e->pin_job_total;
+    p.job_cap = (uint32_t)std::min<size_t>((size_t)e->pin_job_steps * N, 0xffffffffu);
+    int rc = pin_dispatch(e, false, st, p);
+    if (rc) return rc;
+    CU(cudaGetLastError());
+    RewardListParams r;
+    memset(&r, 0, sizeof r);
+    r.d = e->d; r.base = e->base; r.res_stride = (uint32_t)e->res_stride; r.n_envs = e->n_envs;
+    r.jobs = e->pin_jobs; r.job_total = e->pin_job_total; r.job_cap = p.job_cap;
+    r.reward_log = p.reward_log; r.step_no = e->step_no; r.stats = e->stats;
+    r.final_from = std::max(0, n_steps - 2 - t0);  // beyond nt when the call goes on after this launch
+    const int want_ctas = (int)std::min<size_t>(((size_t)nt * N + kWarpsPerCta - 1) / kWarpsPerCta,
+                                                (size_t)e->sms * PCB_REWARD_GRID_MULT);
+    reward_list_kernel<<<std::max(1, want_ctas), kWarpsPerCta * 32, e->reward_smem, st>>>(r);
+    CU(cudaGetLastError());
+    e->launches += 2;
+    e->slice = (e->slice + nt) % e->ring;
+    e->step_no += (uint64_t)nt;
+  }
+  if (e->timing) {
+    CU(cudaEventRecord(b, st));
+    CU(cudaEventSynchronize(b));
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    e->fused_ms += ms; e->fused_launches += 1; e->fused_steps += n_steps;
+  }
+  return 0;
+}
+
 static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
 
 // pcb_rollout_random of the per-step kinds as CUDA-graph replays.  One graph = L consecutive
@@ -1230,6 +1369,12 @@ int pcb_rollout_random_logged(pcb_env_t* e, uint64_t seed, int n_steps, int32_t*
   if (e->fused)
     return rollout_fused(e, seed, n_steps, d_actions_log, d_reward_log, d_done_log, (cudaStream_t)stream,
                          nullptr, 0);
+  if (e->fused_pin) {
+    rc = join_rewards(e, (cudaStream_t)stream);  // reward kernels of earlier per-step calls
+    if (rc) return rc;
+    return rollout_pin_fused(e, seed, n_steps, d_actions_log, d_reward_log, d_done_log, (cudaStream_t)stream,
+                             nullptr, 0);
+  }
   const size_t N = (size_t)e->n_envs, per = N * (e->d.kind == 0 ? 2 : 3);
   cudaStream_t st = (cudaStream_t)stream;
   const int total_steps = n_steps;
@@ -1343,10 +1488,14 @@ int pcb_steps_host(pcb_env_t* e, const int32_t* h_actions, int n_steps, int acti
   const size_t per = N * (action_format == PCB_ACTION_FLAT ? 1 : (e->d.kind == 0 ? 2 : 3));
   rc = ensure_host_staging(e, T);
   if (rc) return rc;
-  if (e->fused) {
-    // pin-less kinds: every row up, ONE launch of the multi-step kernel, every result down
+  if (e->fused || e->fused_pin) {
+    // pin-less kinds (and the pin env in its multi-step kernel): every row up, one launch of
+    // the multi-step kernel per chunk of steps, every result down
     CU(cudaMemcpyAsync(e->hs_actions, h_actions, T * per * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    rc = rollout_fused(e, 0, n_steps, nullptr, e->hs_reward, e->hs_done, st, e->hs_actions, action_format);
+    if (e->fused_pin) rc = join_rewards(e, st);
+    if (rc) return rc;
+    rc = e->fused ? rollout_fused(e, 0, n_steps, nullptr, e->hs_reward, e->hs_done, st, e->hs_actions, action_format)
+                  : rollout_pin_fused(e, 0, n_steps, nullptr, e->hs_reward, e->hs_done, st, e->hs_actions, action_format);
     if (rc) return rc;
     CU(cudaMemcpyAsync(h_reward, e->hs_reward, T * N * sizeof(double), cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(h_done, e->hs_done, T * N, cudaMemcpyDeviceToHost, st));
@@ -1433,7 +1582,8 @@ int64_t pcb_check_guards(pcb_env_t* e, void* stream) {
 int pcb_set_fused_rollout(pcb_env_t* e, int on) {
   if (!e) return fail(PCB_ERR_INVALID, "env is NULL");
   e->fused = on != 0 && e->d.kind <= 1 && !e->wide;
-  return e->fused ? 1 : 0;
+  e->fused_pin = on != 0 && e->fused_pin_ok;  // on: also for batches above the default threshold
+  return (e->fused || e->fused_pin) ? 1 : 0;
 }
 
 int pcb_fused_rollout_times(pcb_env_t* e, double* ms, int64_t* launches, int64_t* steps) {

@@ -157,8 +157,8 @@ def test_reference_dtype_mode_equals_the_oracle_value_for_value(name):
     env.close()
 
 
-def test_fused_rollout_is_refused_for_pin_kinds_and_wide_boards():
-    for name in ("C", "S_wide_sq", "S_wide_rect"):
+def test_fused_rollout_is_refused_for_beam_rewards_spatial_and_wide_boards():
+    for name in ("C_both", "D", "S_wide_pin", "S_wide_sq", "S_wide_rect"):
         env = make(name, 8)
         assert not env.fused_rollout(True)
         env.close()
@@ -535,6 +535,7 @@ def test_graph_rollout_equals_plain_launches(name, ring):
     a = make(name, n, seed=9, obs_ring=ring, bank_size=3 * n)
     b = make(name, n, seed=9, obs_ring=ring, bank_size=3 * n)
     b.graph_rollout(False)
+    a.fused_rollout(False); b.fused_rollout(False)  # the per-step launches are what a graph replays
     a.reset(); b.reset()
     torch.cuda.synchronize()
     with torch.cuda.stream(torch.cuda.Stream()):  # the default stream cannot be captured
@@ -572,3 +573,61 @@ def _graph_rollout_body(name, n, a, b):
         e.step(e.sample_random_actions(seed=1))  # plain step in between
         e.rollout_random(37, seed=6)
     same("third")
+
+
+@pytest.mark.parametrize("name", ["C", "REF_pin", "S_pin_tight", "S_pin_cen", "FZ_rect_pin_0_cen",
+                                  "FZ_rect_pin_3_cen", "FZ_rect_pin_4_cen", "FZ_rect_pin_6_cen"])
+@pytest.mark.parametrize("autoreset", [True, False])
+def test_pin_fused_rollout_equals_per_step(name, autoreset):
+    """rollout_pin_kernel (many steps per launch, 32/LPE envs per warp, rewards from a job list
+    afterwards) against the per-step kernels: every observation slice, the logged actions,
+    rewards and dones of every step, the state records, the result tensors and the statistics."""
+    cfg = CONFIGS[name]
+    if cfg["type"] != "rectangle_pin" or cfg["reward_type"] != "centroid" or max(cfg["height"], cfg["width"]) > 32:
+        pytest.skip("not a configuration of the fused pin kernel")
+    n, T = 203, 41
+    a = make(name, n, seed=11, obs_ring=T + 1, bank_size=5 * n, autoreset=autoreset)
+    b = make(name, n, seed=11, obs_ring=T + 1, bank_size=5 * n, autoreset=autoreset)
+    assert a.fused_rollout(True)
+    b.fused_rollout(False)
+    a.reset(); b.reset()
+    logs = []
+    for e in (a, b):
+        al = torch.zeros((T, n, 3), dtype=torch.int32, device="cuda")
+        rl = torch.full((T, n), -7.0, dtype=torch.float64, device="cuda")
+        dl = torch.zeros((T, n), dtype=torch.uint8, device="cuda")
+        e.rollout_random(T, seed=3, actions_log=al, reward_log=rl, done_log=dl)
+        logs.append((al, rl, dl))
+    torch.cuda.synchronize()
+    for x, y, what in zip(logs[0], logs[1], ("actions", "reward", "done")):
+        assert torch.equal(x, y), (name, what, (x != y).nonzero()[:5].tolist())
+    assert int(logs[0][2].sum()) > 0
+
+    def same(tag):
+        torch.cuda.synchronize()
+        for k in a.obs_ring_tensors:
+            assert torch.equal(a.obs_ring_tensors[k], b.obs_ring_tensors[k]), (name, tag, k)
+        assert np.array_equal(a.state_dict()["state"], b.state_dict()["state"]), (name, tag)
+        ra, rb = a.results(), b.results()
+        done = ra["done"].bool()
+        assert torch.equal(ra["done"], rb["done"]) and torch.equal(ra["reward"], rb["reward"]), (name, tag)
+        for k in ("wirelength", "num_intersections", "episode_return", "episode_length"):
+            assert torch.equal(ra[k][done], rb[k][done]), (name, tag, k)
+        sa, sb = a.episode_stats(), b.episode_stats()
+        for k in sa:
+            assert sa[k] == sb[k] if k in ("episodes", "steps", "sum_length") else np.isclose(sa[k], sb[k], rtol=1e-12), (name, tag, k)
+
+    same("logged")
+    for e in (a, b):                      # no logs, a length that needs several launches
+        e.rollout_random(150, seed=4)
+        e.step(e.sample_random_actions(seed=9))   # a per-step call in between shares the state
+        e.rollout_random(7, seed=5)
+    same("plain")
+    # the caller's actions through the same kernel (pcb_steps_host)
+    acts = logs[0][0][:9].cpu().pin_memory()
+    Ra, Da = torch.zeros((9, n), dtype=torch.float64), torch.zeros((9, n), dtype=torch.uint8)
+    Rb, Db = torch.zeros((9, n), dtype=torch.float64), torch.zeros((9, n), dtype=torch.uint8)
+    a.steps_host(acts, Ra, Da); b.steps_host(acts, Rb, Db)
+    assert torch.equal(Ra, Rb) and torch.equal(Da, Db), name
+    same("given actions")
+    a.close(); b.close()

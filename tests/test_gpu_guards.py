@@ -35,6 +35,10 @@ def test_no_store_leaves_its_buffer(guarded, name):
                                    bank_size=2 * n, force_generic=generic)
             env.reset()
             env.rollout_random(23, seed=1)
+            if env.kind == "rectangle_pin":   # both rollout paths of the pin env
+                env.fused_rollout(False)
+                env.rollout_random(9, seed=6)
+                env.fused_rollout(True)
             log = torch.zeros((5, n, env.spec.action_width), dtype=torch.int32, device="cuda")
             rl = torch.zeros((5, n), dtype=torch.float64, device="cuda")
             dl = torch.zeros((5, n), dtype=torch.uint8, device="cuda")

@@ -73,3 +73,14 @@ def test_reference_shipped_configs(name):
     run_parity(name, range(16), autoreset=True, episodes=3, stats=st)
     run_parity(name, range(8), force_generic=True, stats=st)
     assert st["reward_inexact"] == 0, st
+
+
+@pytest.mark.parametrize("name", ["C", "REF_pin", "S_pin_tight", "S_pin_cen", "FZ_rect_pin_0_cen",
+                                  "FZ_rect_pin_3_cen", "FZ_rect_pin_4_cen", "FZ_rect_pin_6_cen"])
+def test_pin_rollout_kernel_against_oracle(name):
+    """pcb_rollout_random of the pin env in its multi-step kernel (pcb_pin_small.cuh: 8 / 16 / 32
+    lanes per env, compile-time and runtime shapes): the logged actions replayed through the
+    oracle, every observation of every step, rewards, dones and the episode count."""
+    from parity import run_rollout_parity
+
+    assert run_rollout_parity(name, N=27, T=45, episodes=8) == 27 * 45
