@@ -670,7 +670,9 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
     // per-step kernels (one warp per env either way, and the reward kernel overlaps the next
     // step there instead of running after the rollout).
     const int lpe = small_lanes_per_env(d.H);
-    int max_envs = 32768;
+    // measured on config C (profiles/README.md): 4 096 envs 6.0e8 against 3.2e8 env-steps/s
+    // per-step, 16 384 envs 6.3e8 against 6.7e8 -- the crossover is near 8 192
+    int max_envs = 8192;
     if (const char* f = getenv("PCB_PIN_FUSED_MAX_ENVS")) max_envs = atoi(f);
     e->fused_pin_ok = true;
     e->fused_pin = lpe < 32 || num_envs <= max_envs;

@@ -134,19 +134,33 @@ __device__ __forceinline__ void sample_action_g(const S& sh, uint32_t m0, uint32
   ay = have ? col : 0;
 }
 
-// one board (bit row per lane) -> H*W bytes of 0/1
+// one board (bit row per lane) -> H*W bytes of 0/1; dup_off != 0 writes a second copy at
+// dst + dup_off (orientations 2, 3 of the pin env repeat 0, 1)
 template <int LPE, typename S>
 __device__ __forceinline__ void write_board_g(const S& sh, uint8_t* dst, uint32_t bits, uint32_t* flat,
-                                              int sl, bool live, const uint2* lut) {
+                                              int sl, bool live, const uint2* lut, int dup_off = 0) {
   const int H = sh.H(), W = sh.W();
   if (W == 16) {
-    if (live && sl < H) st_stream(reinterpret_cast<uint4*>(dst) + sl, expand16(lut, bits));
+    if (live && sl < H) {
+      const uint4 v = expand16(lut, bits);
+      st_stream(reinterpret_cast<uint4*>(dst) + sl, v);
+      if (dup_off) st_stream(reinterpret_cast<uint4*>(dst + dup_off) + sl, v);
+    }
   } else if (W == 8) {
-    if (live && sl < H) st_stream(reinterpret_cast<uint2*>(dst) + sl, lut[bits & 0xffu]);
+    if (live && sl < H) {
+      const uint2 v = lut[bits & 0xffu];
+      st_stream(reinterpret_cast<uint2*>(dst) + sl, v);
+      if (dup_off) st_stream(reinterpret_cast<uint2*>(dst + dup_off) + sl, v);
+    }
   } else if (W == 32) {
     if (live && sl < H) {
-      st_stream(reinterpret_cast<uint4*>(dst) + 2 * sl, expand16(lut, bits));
-      st_stream(reinterpret_cast<uint4*>(dst) + 2 * sl + 1, expand16(lut, bits >> 16));
+      const uint4 a = expand16(lut, bits), b = expand16(lut, bits >> 16);
+      st_stream(reinterpret_cast<uint4*>(dst) + 2 * sl, a);
+      st_stream(reinterpret_cast<uint4*>(dst) + 2 * sl + 1, b);
+      if (dup_off) {
+        st_stream(reinterpret_cast<uint4*>(dst + dup_off) + 2 * sl, a);
+        st_stream(reinterpret_cast<uint4*>(dst + dup_off) + 2 * sl + 1, b);
+      }
     }
   } else {
     // dense bit string (bit row*W + col) in shared memory, then 16 / 4 / 1 bits per lane
@@ -162,13 +176,23 @@ __device__ __forceinline__ void write_board_g(const S& sh, uint8_t* dst, uint32_
     __syncwarp();
     if (live) {
       if ((nbits & 15) == 0) {
-        for (int q = sl; q < (nbits >> 4); q += LPE)
-          st_stream(reinterpret_cast<uint4*>(dst) + q, expand16(lut, flat[q >> 1] >> (16 * (q & 1))));
+        for (int q = sl; q < (nbits >> 4); q += LPE) {
+          const uint4 v = expand16(lut, flat[q >> 1] >> (16 * (q & 1)));
+          st_stream(reinterpret_cast<uint4*>(dst) + q, v);
+          if (dup_off) st_stream(reinterpret_cast<uint4*>(dst + dup_off) + q, v);
+        }
       } else if ((nbits & 3) == 0) {
-        for (int q = sl; q < (nbits >> 2); q += LPE)
-          st_stream(reinterpret_cast<uint32_t*>(dst) + q, spread4((flat[q >> 3] >> (4 * (q & 7))) & 15u));
+        for (int q = sl; q < (nbits >> 2); q += LPE) {
+          const uint32_t v = spread4((flat[q >> 3] >> (4 * (q & 7))) & 15u);
+          st_stream(reinterpret_cast<uint32_t*>(dst) + q, v);
+          if (dup_off) st_stream(reinterpret_cast<uint32_t*>(dst + dup_off) + q, v);
+        }
       } else {
-        for (int b = sl; b < nbits; b += LPE) st_stream(dst + b, (uint8_t)((flat[b >> 5] >> (b & 31)) & 1u));
+        for (int b = sl; b < nbits; b += LPE) {
+          const uint8_t v = (uint8_t)((flat[b >> 5] >> (b & 31)) & 1u);
+          st_stream(dst + b, v);
+          if (dup_off) st_stream(dst + dup_off + b, v);
+        }
       }
     }
     __syncwarp();
