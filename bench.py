@@ -33,6 +33,7 @@ ENVS_PER_GPU = 65536
 DEFAULT_ENVS = {"A": 65536, "B": 4096, "C": 65536, "D": 65536, "E": 131072, "C_both": 65536,
                 "C_beam": 65536, "REF_pin": 65536, "REF_rect": 65536, "REF_spatial": 65536,
                 "REF_square": 65536}
+TRAFFIC_ENVS = {"B": 65536, "C": 65536, "D": 65536, "E": 131072}  # profiles/traffic.json
 SECONDARY = ("B", "D", "E")  # BASELINE.json configs[1], [3], [4] at their BASELINE sizes
 OBS_RING = 4
 REPETITIONS = 5
@@ -461,7 +462,7 @@ def measure(args, ctx, name, N, main):
     alone_s = kt_alone["step"][0] * 1e-3 / max(kt_alone["step"][1], 1)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath) and N == DEFAULT_ENVS.get(name):  # captures taken at the default sizes
+    if os.path.exists(tpath) and N == TRAFFIC_ENVS.get(name):  # env counts the ncu captures were taken at
         with open(tpath) as f:
             traffic = json.load(f).get(f"{name}:step_kernel")
     e2e_path = ("pcb_steps_host (C ABI, PcbVecEnv.steps_host), %d action rows per call: each step's flat "

@@ -123,9 +123,9 @@ struct pcb_env {
   // per launch, 32/LPE envs per warp, terminal rewards from a job list afterwards
   bool fused_pin, fused_pin_ok;
   size_t pin_smem;       // dynamic shared memory per CTA (4 warps)
-  uint8_t* pin_jobs;     // job list of one launch, pin_job_steps * N records
-  uint32_t* pin_job_total;
-  int pin_job_steps;     // steps per launch the list is sized for
+  uint8_t* pin_jobs[2];  // job lists of two launches in flight, pin_job_steps * N records each
+  uint32_t* pin_job_total[2];
+  int pin_job_steps;     // steps per launch a list is sized for
   size_t small_smem;     // its dynamic shared memory per CTA
   double fused_ms;       // timing (pcb_enable_kernel_timing): device time, launches, env-steps
   int64_t fused_launches, fused_steps;
@@ -652,8 +652,9 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
       else TRY((set_smem_shape<1, uint32_t, DynShape>(e->smem_bytes)));
   }
   e->fused = d.kind <= 1 && !e->wide;
-  e->fused_pin = false; e->fused_pin_ok = false; e->pin_smem = 0; e->pin_jobs = nullptr;
-  e->pin_job_total = nullptr; e->pin_job_steps = 0;
+  e->fused_pin = false; e->fused_pin_ok = false; e->pin_smem = 0;
+  e->pin_jobs[0] = e->pin_jobs[1] = nullptr;
+  e->pin_job_total[0] = e->pin_job_total[1] = nullptr; e->pin_job_steps = 0;
   e->sms = 148;
   cudaDeviceGetAttribute(&e->sms, cudaDevAttrMultiProcessorCount, device);
   e->small_smem = 0; e->fused_ms = 0.0; e->fused_launches = 0; e->fused_steps = 0;
@@ -671,8 +672,8 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
     // step there instead of running after the rollout).
     const int lpe = small_lanes_per_env(d.H);
     // measured on config C (profiles/README.md): 4 096 envs 6.0e8 against 3.2e8 env-steps/s
-    // per-step, 16 384 envs 6.3e8 against 6.7e8 -- the crossover is near 8 192
-    int max_envs = 8192;
+    // per-step, 12 288 envs 6.4e8 against 6.3e8, 16 384 envs 6.2e8 against 6.7e8
+    int max_envs = 12288;
     if (const char* f = getenv("PCB_PIN_FUSED_MAX_ENVS")) max_envs = atoi(f);
     e->fused_pin_ok = true;
     e->fused_pin = lpe < 32 || num_envs <= max_envs;
@@ -802,7 +803,7 @@ int pcb_destroy(pcb_env_t* e) {
   if (e->copy) cudaStreamDestroy(e->copy);
   if (e->ev_host) cudaEventDestroy(e->ev_host);
   for (cudaEvent_t ev : e->hs_events) cudaEventDestroy(ev);
-  if (e->pin_jobs) cudaFree(e->pin_jobs);
+  if (e->pin_jobs[0]) cudaFree(e->pin_jobs[0]);
   if (e->hs_actions) cudaFree(e->hs_actions);
   if (e->hs_reward) cudaFree(e->hs_reward);
   if (e->hs_done) cudaFree(e->hs_done);
@@ -1180,7 +1181,10 @@ static int rollout_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_ac
 }
 
 // the pin env: n_steps in launches of up to pin_job_steps steps of rollout_pin_kernel, each
-// followed by reward_list_kernel over the routing jobs it left.  d_actions != nullptr: the
+// followed by reward_list_kernel over the routing jobs it left -- on the side stream, so the
+// rewards of launch k are computed while launch k+1 steps (two job lists alternate).  Cutting a
+// call into more, shorter launches to overlap more was measured and is slower (C at 4 096 envs
+// 6.0e8 -> 5.4e8 env-steps/s with 4 launches per 128 steps).  d_actions != nullptr: the
 // caller's action rows instead of the random policy (pcb_steps_host).
 static int rollout_pin_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_actions_log,
                              double* d_reward_log, uint8_t* d_done_log, cudaStream_t st,
@@ -1188,20 +1192,27 @@ static int rollout_pin_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* 
   CU(cudaSetDevice(e->device));
   const size_t N = (size_t)e->n_envs;
   const size_t jstride = (size_t)job_stride(e->d.max_pins, e->d.K);
-  // the list must hold a job per env and step (every env can finish an episode every step
-  // when its instance has one component): at most 256 MB, at most 64 steps per launch
+  // a list must hold a job per env and step (every env can finish an episode every step when
+  // its instance has one component): at most 256 MB each, at most 64 steps per launch
   const int want = (int)std::max<size_t>(1, std::min<size_t>(64, (256u << 20) / (N * jstride)));
-  if (!e->pin_jobs || e->pin_job_steps < std::min(want, n_steps)) {
-    CU(cudaStreamSynchronize(st));
-    if (e->pin_jobs) { cudaFree(e->pin_jobs); e->pin_jobs = nullptr; }
+  if (!e->pin_jobs[0]) {
+    const size_t list = (size_t)want * N * jstride;
     void* q = nullptr;
-    cudaError_t err = cudaMalloc(&q, (size_t)want * N * jstride + 16);
+    cudaError_t err = cudaMalloc(&q, 2 * list + 32);
     if (err != cudaSuccess)
-      return fail(err == cudaErrorMemoryAllocation ? PCB_ERR_NOMEM : PCB_ERR_CUDA, "job list: %s", cudaGetErrorString(err));
-    e->pin_jobs = (uint8_t*)q;
-    e->pin_job_total = reinterpret_cast<uint32_t*>(e->pin_jobs + (size_t)want * N * jstride);
+      return fail(err == cudaErrorMemoryAllocation ? PCB_ERR_NOMEM : PCB_ERR_CUDA, "job lists: %s", cudaGetErrorString(err));
+    e->pin_jobs[0] = (uint8_t*)q;
+    e->pin_jobs[1] = e->pin_jobs[0] + list;
+    e->pin_job_total[0] = reinterpret_cast<uint32_t*>(e->pin_jobs[0] + 2 * list);
+    e->pin_job_total[1] = e->pin_job_total[0] + 4;
     e->pin_job_steps = want;
   }
+  const int chunk = e->pin_job_steps;
+  // the reward kernel of launch k runs on the side stream beside launch k+1 (measured with
+  // PCB_PIN_OVERLAP=0/1: C at 4 096 envs 5.9e8 -> 6.4e8, REF_pin 1.09e9 -> 1.13e9, C at 8 192
+  // envs 6.4e8 -> 6.2e8)
+  bool overlap = e->overlap;
+  if (const char* f = getenv("PCB_PIN_OVERLAP")) overlap = atoi(f) != 0;  // experiments
   const size_t per = N * (action_format == PCB_ACTION_FLAT ? 1 : 3);
   cudaEvent_t a = nullptr, b = nullptr;
   if (e->timing) {
@@ -1209,9 +1220,14 @@ static int rollout_pin_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* 
     CU(cudaEventCreate(&b));
     CU(cudaEventRecord(a, st));
   }
-  for (int t0 = 0; t0 < n_steps; t0 += e->pin_job_steps) {
-    const int nt = std::min(e->pin_job_steps, n_steps - t0);
-    CU(cudaMemsetAsync(e->pin_job_total, 0, sizeof(uint32_t), st));
+  int k = 0;
+  for (int t0 = 0; t0 < n_steps; t0 += chunk, ++k) {
+    const int nt = std::min(chunk, n_steps - t0), buf = k & 1;
+    if (e->rew_pending[buf]) {  // the reward kernel of launch k-2 still reads this list
+      CU(cudaStreamWaitEvent(st, e->ev_rew[buf], 0));
+      e->rew_pending[buf] = false;
+    }
+    CU(cudaMemsetAsync(e->pin_job_total[buf], 0, sizeof(uint32_t), st));
     PinRolloutParams p;
     memset(&p, 0, sizeof p);
     p.d = e->d; p.base = e->base;
@@ -1225,7 +1241,7 @@ static int rollout_pin_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* 
     p.seed = seed; p.step_no = e->step_no; p.bank_count = e->bank_count;
     p.slot_step = e->bank_count ? (uint32_t)e->n_envs % e->bank_count : (uint32_t)e->n_envs;
     p.n_envs = e->n_envs; p.n_steps = nt; p.ring = e->ring; p.slice0 = e->slice;
-    p.jobs = e->pin_jobs; p.job_total = e->pin_job_total;
+    p.jobs = e->pin_jobs[buf]; p.job_total = e->pin_job_total[buf];
     p.job_cap = (uint32_t)std::min<size_t>((size_t)e->pin_job_steps * N, 0xffffffffu);
     int rc = pin_dispatch(e, false, st, p);
     if (rc) return rc;
@@ -1233,17 +1249,28 @@ static int rollout_pin_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* 
     RewardListParams r;
     memset(&r, 0, sizeof r);
     r.d = e->d; r.base = e->base; r.res_stride = (uint32_t)e->res_stride; r.n_envs = e->n_envs;
-    r.jobs = e->pin_jobs; r.job_total = e->pin_job_total; r.job_cap = p.job_cap;
+    r.jobs = e->pin_jobs[buf]; r.job_total = e->pin_job_total[buf]; r.job_cap = p.job_cap;
     r.reward_log = p.reward_log; r.step_no = e->step_no; r.stats = e->stats;
     r.final_from = std::max(0, n_steps - 2 - t0);  // beyond nt when the call goes on after this launch
     const int want_ctas = (int)std::min<size_t>(((size_t)nt * N + kWarpsPerCta - 1) / kWarpsPerCta,
                                                 (size_t)e->sms * PCB_REWARD_GRID_MULT);
-    reward_list_kernel<<<std::max(1, want_ctas), kWarpsPerCta * 32, e->reward_smem, st>>>(r);
-    CU(cudaGetLastError());
+    if (overlap) {
+      CU(cudaEventRecord(e->ev_step[buf], st));
+      CU(cudaStreamWaitEvent(e->side, e->ev_step[buf], 0));
+      reward_list_kernel<<<std::max(1, want_ctas), kWarpsPerCta * 32, e->reward_smem, e->side>>>(r);
+      CU(cudaGetLastError());
+      CU(cudaEventRecord(e->ev_rew[buf], e->side));
+      e->rew_pending[buf] = true;
+    } else {
+      reward_list_kernel<<<std::max(1, want_ctas), kWarpsPerCta * 32, e->reward_smem, st>>>(r);
+      CU(cudaGetLastError());
+    }
     e->launches += 2;
     e->slice = (e->slice + nt) % e->ring;
     e->step_no += (uint64_t)nt;
   }
+  int rc = join_rewards(e, st);
+  if (rc) return rc;
   if (e->timing) {
     CU(cudaEventRecord(b, st));
     CU(cudaEventSynchronize(b));

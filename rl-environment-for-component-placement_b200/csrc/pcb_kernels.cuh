@@ -1089,6 +1089,9 @@ __device__ __forceinline__ int count_crossings(const RouteScratch& rs, int lane,
   int cnt = 0, qn = 0;
   auto heavy = [&](uint32_t pr) -> int {
     int s = pr >> 16, t = pr & 0xffffu;
+#ifdef PCB_EXP_NO_HEAVY  // sensitivity experiment only (wrong rewards): the filter without the float64 test
+    return (s + t) & 1;
+#endif
     return segments_cross((double)rs.px[s], (double)rs.py[s], rs.x2[s], rs.y2[s],
                           (double)rs.px[t], (double)rs.py[t], rs.x2[t], rs.y2[t]) ? 1 : 0;
   };
@@ -1141,7 +1144,11 @@ __device__ __forceinline__ void centroid_route(const Dims& d, const RouteScratch
     rs.x2[q] = x2; rs.y2[q] = y2; rs.box[q] = box; rs.dist[q] = len;
   }
   __syncwarp();
+#ifdef PCB_EXP_NO_CROSS  // sensitivity experiment only (wrong rewards): how much of the interference is the crossing count?
+  crossings = 0;
+#else
   crossings = count_crossings(rs, lane, n_pins);
+#endif
   // find_wirelength (pin:741-759): the reference's sequential float64 sum, net by net.
   // Every lane runs the same chain; the operands come from registers via shuffles so
   // only the additions are dependent.

@@ -422,8 +422,18 @@ rollout_pin_kernel(const __grid_constant__ PinRolloutParams p) {
     write_board_g<LPE, S>(sh, p.base.grid + (size_t)se * HW, occ, flat, sl, live, lut);
     uint8_t* mk = p.base.mask + (size_t)se * (uint32_t)(4 * HW);
     // orientations 2, 3 repeat 0, 1 (pin:1868-1869)
-    write_board_g<LPE, S>(sh, mk, m0, flat, sl, live, lut, 2 * HW);
-    write_board_g<LPE, S>(sh, mk + HW, m1, flat, sl, live, lut, 2 * HW);
+    if (W == 8 || W == 16 || W == 32) {
+      // register -> table -> store boards: expanding twice beats storing one expansion twice
+      // (measured, C at 8 192 envs: 6.4e8 against 5.6e8 env-steps/s)
+      write_board_g<LPE, S>(sh, mk, m0, flat, sl, live, lut);
+      write_board_g<LPE, S>(sh, mk + HW, m1, flat, sl, live, lut);
+      write_board_g<LPE, S>(sh, mk + 2 * HW, m0, flat, sl, live, lut);
+      write_board_g<LPE, S>(sh, mk + 3 * HW, m1, flat, sl, live, lut);
+    } else {
+      // dense-bit-string boards: pack once, store both copies (REF_pin: 1.07e9 -> 1.13e9)
+      write_board_g<LPE, S>(sh, mk, m0, flat, sl, live, lut, 2 * HW);
+      write_board_g<LPE, S>(sh, mk + HW, m1, flat, sl, live, lut, 2 * HW);
+    }
     copy_out_g<LPE>(p.base.feat + (size_t)se * (uint32_t)(C * 5), ifeat, C * 20, sl, live);
     copy_out_g<LPE>(p.base.pnum + (size_t)se * (uint32_t)(C * P * 4), inum, C * P * 8, sl, live);
     copy_out_g<LPE>(p.base.pcat + (size_t)se * (uint32_t)(C * P), icat, C * P * 2, sl, live);
