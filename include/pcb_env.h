@@ -175,11 +175,14 @@ int pcb_step(pcb_env_t* env, const int32_t* d_actions, int action_format, void* 
 int pcb_sample_random_actions(pcb_env_t* env, uint64_t seed, int32_t* d_actions, void* stream);
 
 /* step() through HOST buffers: copies h_actions (ideally pinned) to the device,
- * steps, copies reward[N] (f64) and done[N] (u8) back and waits for them.  When the two
- * result buffers are one packed block -- h_done == (uint8_t*)(h_reward + N) -- both come
- * back in ONE device-to-host copy (the library keeps them side by side on the device). */
+ * steps, copies reward[N] (f64) and done[N] (u8) back and waits for them.
+ * pcb_step_host_packed: the results arrive in ONE block h_result = [reward f64 x N | done u8 x N]
+ * (N * 9 bytes, one allocation) with a single device-to-host copy -- the library keeps the two
+ * side by side on the device. */
 int pcb_step_host(pcb_env_t* env, const int32_t* h_actions, int action_format,
                   double* h_reward, uint8_t* h_done, void* stream);
+int pcb_step_host_packed(pcb_env_t* env, const int32_t* h_actions, int action_format,
+                         void* h_result, void* stream);
 
 /* n_steps calls of step() for a caller that already holds the action rows (replay of a
  * recorded rollout, evaluation of a fixed plan, a policy that emits several rows at once):

@@ -15,7 +15,7 @@ SYMBOLS = (
     "pcb_kernel_times", "pcb_current_result_half", "pcb_generate_host", "pcb_generate_instances_device", "pcb_state_layout", "pcb_get_state",
     "pcb_set_state", "pcb_set_reward_overlap", "pcb_shape_id", "pcb_set_fused_rollout",
     "pcb_fused_rollout_times", "pcb_rollout_random_logged", "pcb_check_guards", "pcb_steps_host",
-    "pcb_set_graph_rollout", "pcb_graph_replays",
+    "pcb_set_graph_rollout", "pcb_graph_replays", "pcb_step_host_packed",
 )
 
 
@@ -74,6 +74,7 @@ def load(path=None):
     lib.pcb_sample_random_actions.argtypes = [vp, u64, vp, vp]
     lib.pcb_step_host.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.pcb_steps_host.argtypes = [vp, vp, i32, i32, vp, vp, vp]
+    lib.pcb_step_host_packed.argtypes = [vp, vp, i32, vp, vp]
     lib.pcb_get_tensor.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
     lib.pcb_current_slice.argtypes = [vp]
     lib.pcb_current_result_half.argtypes = [vp]

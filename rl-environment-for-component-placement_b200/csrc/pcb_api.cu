@@ -1011,11 +1011,11 @@ int pcb_sample_random_actions(pcb_env_t* e, uint64_t seed, int32_t* d_actions, v
   return launch(e, K_SAMPLE, p, (cudaStream_t)stream);
 }
 
-int pcb_step_host(pcb_env_t* e, const int32_t* h_actions, int action_format, double* h_reward,
-                  uint8_t* h_done, void* stream) {
+static int step_host_impl(pcb_env_t* e, const int32_t* h_actions, int action_format, double* h_reward,
+                          uint8_t* h_done, bool packed, void* stream) {
   int rc = ready(e);
   if (rc) return rc;
-  if (!h_actions || !h_reward || !h_done) return fail(PCB_ERR_INVALID, "NULL host buffer");
+  if (!h_actions || !h_reward || (!packed && !h_done)) return fail(PCB_ERR_INVALID, "NULL host buffer");
   CU(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream;
   size_t per = action_format == PCB_ACTION_FLAT ? 1 : (e->d.kind == 0 ? 2 : 3);
@@ -1025,7 +1025,7 @@ int pcb_step_host(pcb_env_t* e, const int32_t* h_actions, int action_format, dou
   // the half the step just wrote: [reward f64 x N | done u8 x N] contiguous on the device
   const size_t N = (size_t)e->n_envs;
   const uint8_t* blk = reinterpret_cast<const uint8_t*>(e->base.reward) + (size_t)((e->step_no + 1) & 1) * e->res_stride;
-  if (h_done == reinterpret_cast<uint8_t*>(h_reward + N)) {  // packed host buffer: one copy
+  if (packed) {
     CU(cudaMemcpyAsync(h_reward, blk, N * 9, cudaMemcpyDeviceToHost, st));
   } else {
     CU(cudaMemcpyAsync(h_reward, blk, N * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -1033,6 +1033,16 @@ int pcb_step_host(pcb_env_t* e, const int32_t* h_actions, int action_format, dou
   }
   CU(cudaStreamSynchronize(st));
   return 0;
+}
+
+int pcb_step_host(pcb_env_t* e, const int32_t* h_actions, int action_format, double* h_reward,
+                  uint8_t* h_done, void* stream) {
+  return step_host_impl(e, h_actions, action_format, h_reward, h_done, false, stream);
+}
+
+int pcb_step_host_packed(pcb_env_t* e, const int32_t* h_actions, int action_format, void* h_result,
+                         void* stream) {
+  return step_host_impl(e, h_actions, action_format, reinterpret_cast<double*>(h_result), nullptr, true, stream);
 }
 
 int pcb_get_tensor(pcb_env_t* e, const char* key, DLManagedTensor** out) {

@@ -55,9 +55,10 @@ class HostStepper:
         n = env.num_envs
         if tuple(actions.shape[1:]) not in ((n,), (n, env.spec.action_width)):
             raise ValueError("actions must have shape [T, N] or [T, N, k]")
-        if reward is None and done is None:
-            # one packed pinned block [reward f64 x N | done u8 x N]: the library then needs a
-            # single device-to-host copy per step (pcb_step_host)
+        self._packed = reward is None and done is None
+        if self._packed:
+            # one packed pinned block [reward f64 x N | done u8 x N]: a single device-to-host
+            # copy per step (pcb_step_host_packed)
             self.result = torch.empty(n * 9, dtype=torch.uint8, pin_memory=True)
             reward = self.result[: n * 8].view(torch.float64)
             done = self.result[n * 8:]
@@ -65,7 +66,8 @@ class HostStepper:
             raise ValueError("reward and done must have shape [N]")
         self.reward, self.done = reward, done
         self._keep = (actions, reward, done)  # the buffers must outlive the stepper
-        self._env, self._fn, self._h = env, env.lib.pcb_step_host, env._h
+        self._env, self._h = env, env._h
+        self._fn = env.lib.pcb_step_host_packed if self._packed else env.lib.pcb_step_host
         self._fmt = 1 if len(actions.shape) == 2 else 0
         row = n * (1 if self._fmt else env.spec.action_width) * 4
         self._a0, self._row = _host_buffer(actions, "int32", "actions"), row
@@ -76,7 +78,10 @@ class HostStepper:
     def __call__(self, t):
         if not 0 <= t < self._steps:
             raise IndexError(t)
-        rc = self._fn(self._h, self._a0 + t * self._row, self._fmt, self._r, self._d, self._stream)
+        if self._packed:
+            rc = self._fn(self._h, self._a0 + t * self._row, self._fmt, self._r, self._stream)
+        else:
+            rc = self._fn(self._h, self._a0 + t * self._row, self._fmt, self._r, self._d, self._stream)
         if rc < 0:
             self._env._check(rc)
 

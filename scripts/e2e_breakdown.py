@@ -18,7 +18,7 @@ from pcbgpu.configs import CONFIGS  # noqa: E402
 if os.environ.get("USE_STREAM"):
     torch.cuda.set_stream(torch.cuda.Stream())
 NAME = sys.argv[1] if len(sys.argv) > 1 else "C"
-N, K = int(sys.argv[2]) if len(sys.argv) > 2 else 65536, 200
+N, K = int(sys.argv[2]) if len(sys.argv) > 2 else 65536, 192
 env = pcbgpu.PcbVecEnv(CONFIGS[NAME], N, autoreset=True, obs_ring=4, bank_size=4 * N, seed=1,
                        generate_on_device=True)
 env.reset()
@@ -85,6 +85,21 @@ run("pcb_step, device actions, no sync", no_sync)
 run("pcb_step, device actions, sync every step", dev_only)
 run("+ H2D of the actions (torch copy)", with_h2d)
 run("+ D2H of reward and done (torch copies)", with_both)
-run("pcb_step_host", step_host)
+run("pcb_step_host, two result buffers (two D2H copies)", step_host)
 stepper = env.host_stepper(h_act, h_r, h_d)
 run("pcb_step_host through host_stepper (pointers bound once)", stepper)
+packed = env.host_stepper(h_act)
+run("pcb_step_host, packed result block (one D2H copy)", packed)
+# pcb_steps_host: ROWS action rows per call, copies overlapped with the neighbouring steps
+ROWS = 32
+h_R = torch.empty((K, N), dtype=torch.float64, pin_memory=True)
+h_D = torch.empty((K, N), dtype=torch.uint8, pin_memory=True)
+env.steps_host(h_act[:ROWS], h_R[:ROWS], h_D[:ROWS])
+
+
+def rows_host(t):
+    if t % ROWS == 0:
+        env.steps_host(h_act[t:t + ROWS], h_R[t:t + ROWS], h_D[t:t + ROWS])
+
+
+run("pcb_steps_host, %d rows per call" % ROWS, rows_host)

@@ -631,3 +631,22 @@ def test_pin_fused_rollout_equals_per_step(name, autoreset):
     assert torch.equal(Ra, Rb) and torch.equal(Da, Db), name
     same("given actions")
     a.close(); b.close()
+
+
+def test_step_host_with_adjacent_result_buffers():
+    """reward and done buffers that happen to be adjacent in memory (two pinned tensors out of one
+    allocator block) must not be taken for a packed block: the packed copy is its own entry point."""
+    n = 256
+    a, b = make("C", n, seed=3), make("C", n, seed=3)
+    a.reset(); b.reset()
+    blk = torch.empty(n * 9 + 64, dtype=torch.uint8).pin_memory()
+    rew = blk[: n * 8].view(torch.float64)
+    done = blk[n * 8: n * 9]           # starts exactly where the rewards end
+    acts = torch.zeros((6, n), dtype=torch.int32).pin_memory()
+    acts[:] = (torch.arange(n, dtype=torch.int32) * 37) % 3000
+    f = b.host_stepper(acts)           # packed block of its own
+    for t in range(6):
+        a.step_host(acts[t].numpy(), rew.numpy(), done.numpy())
+        f(t)
+        assert np.array_equal(rew.numpy(), f.reward.numpy()) and np.array_equal(done.numpy(), f.done.numpy()), t
+    a.close(); b.close()
