@@ -398,14 +398,16 @@ int pin_dispatch(pcb_env* e, bool configure, cudaStream_t st, const PinRolloutPa
   const int warps = (e->n_envs + G - 1) / G;
   const int wpc = warps <= e->sms * 32 ? 1 : kWarpsPerCta;
   dim3 grid((warps + wpc - 1) / wpc), block(wpc * 32);
-  const PinSmem L = pin_smem_layout(e->d.C, e->d.L.P, e->d.max_pins, e->d.H * e->d.W);
+  const PinSmem L = pin_smem_layout(e->d.kind, e->d.C, e->d.L.P, e->d.max_pins, e->d.H, e->d.W, e->d.K, e->d.mh, e->d.mw);
   const size_t sm = configure ? e->pin_smem : (size_t)kLutBytes + (size_t)L.total * wpc * G;
   switch (e->shape_id) {
     case 2: return pin_launch<ShapeC, 32>(configure, sm, grid, block, st, p);
+    case 3: return pin_launch<ShapeD, 32>(configure, sm, grid, block, st, p);
     case 5: return pin_launch<ShapeRefPin, 16>(configure, sm, grid, block, st, p);
+    case 6: return pin_launch<ShapeRefSpatial, 16>(configure, sm, grid, block, st, p);
 #ifdef PCB_USER_SHAPE
     case 100:
-      if constexpr (kUserDims[0] == 2 && !kUserWide)
+      if constexpr (kUserDims[0] >= 2 && !kUserWide)
         return pin_launch<ShapeUser, small_lanes_per_env(kUserDims[1])>(configure, sm, grid, block, st, p);
       break;
 #endif
@@ -665,7 +667,7 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
     memset(&none, 0, sizeof none);
     TRY(small_dispatch(e, true, nullptr, none));
   }
-  if (d.kind == 2 && !e->wide && d.reward_type == PCB_REWARD_CENTROID && cfg->reserved0 != 1) {
+  if (d.kind >= 2 && !e->wide && d.reward_type == PCB_REWARD_CENTROID && cfg->reserved0 != 1) {
     // Small boards pack several envs into a warp; a small batch of any board is launch- and
     // latency-bound with one launch per step.  A large batch of a 32-row board keeps the
     // per-step kernels (one warp per env either way, and the reward kernel overlaps the next
@@ -673,11 +675,12 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
     const int lpe = small_lanes_per_env(d.H);
     // measured on config C (profiles/README.md): 4 096 envs 6.0e8 against 3.2e8 env-steps/s
     // per-step, 12 288 envs 6.4e8 against 6.3e8, 16 384 envs 6.2e8 against 6.7e8
-    int max_envs = 12288;
+    // spatial env (D): 4 096 envs 2.8e8 against 2.1e8, 8 192 envs 2.7e8 against 3.0e8
+    int max_envs = d.kind == 3 ? 6144 : 12288;
     if (const char* f = getenv("PCB_PIN_FUSED_MAX_ENVS")) max_envs = atoi(f);
     e->fused_pin_ok = true;
     e->fused_pin = lpe < 32 || num_envs <= max_envs;
-    const PinSmem L = pin_smem_layout(d.C, d.L.P, d.max_pins, d.H * d.W);
+    const PinSmem L = pin_smem_layout(d.kind, d.C, d.L.P, d.max_pins, d.H, d.W, d.K, d.mh, d.mw);
     e->pin_smem = (size_t)kLutBytes + (size_t)L.total * kWarpsPerCta * (32 / lpe);
     if (e->pin_smem > 200 * 1024) { e->fused_pin_ok = false; e->fused_pin = false; }
     if (e->fused_pin_ok) {

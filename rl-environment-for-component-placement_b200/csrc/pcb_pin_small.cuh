@@ -1,5 +1,5 @@
-// pcb_pin_small.cuh -- the random-policy rollout of the PIN environment
-// (dummy_env_rectangular_pin.py:1544-1710) as ONE launch for many steps, LPE lanes per
+// pcb_pin_small.cuh -- the random-policy rollout of the PIN environments
+// (dummy_env_rectangular_pin.py:1544-1710, dummy_env_rectangular_pin_spatial.py:1487-1661) as ONE launch for many steps, LPE lanes per
 // environment: the layout of pcb_small.cuh extended to components with pins.
 //
 // Why: the per-step kernels give one warp to an environment and one launch (plus a reward
@@ -53,20 +53,29 @@ struct PinRolloutParams {
   uint32_t job_cap;
 };
 
-// shared memory per environment
+// shared memory per environment: state, the next bank record, the images of the tensors that
+// change a little per step (feature rows, pin rows; spatial env: pin_grid, component_grid)
 struct PinSmem {
-  int comps, pins, nrec, pnum, pcat, feat, flat, total;
+  int comps, pins, orient, nrec, pnum, pcat, feat, pgrid, cgrid, flat, total;
+  int pnum_b, pcat_b, feat_b, pgrid_b, cgrid_b;  // bytes of each image = bytes of one env's slice
 };
-PCB_HD constexpr PinSmem pin_smem_layout(int C, int P, int max_pins, int HW) {
+PCB_HD constexpr PinSmem pin_smem_layout(int kind, int C, int P, int max_pins, int H, int W, int K,
+                                         int mh, int mw) {
   PinSmem s{};
+  const int rows = kind == 3 ? C * P + 1 : C * P, F = kind == 3 ? 5 + P : 5;
+  s.pnum_b = rows * 8; s.pcat_b = kind == 3 ? rows * 4 : rows * 2; s.feat_b = C * F * 4;
+  s.pgrid_b = kind == 3 ? H * W * K : 0; s.cgrid_b = kind == 3 ? C * mh * mw * K : 0;
   s.comps = 0;
   s.pins = s.comps + align16c(C * 4);
-  s.nrec = s.pins + align16c(max_pins * 8);
+  s.orient = s.pins + align16c(max_pins * 8);
+  s.nrec = s.orient + (kind == 3 ? align16c(C) : 0);
   s.pnum = s.nrec + 16 + align16c(C * 4) + align16c(max_pins * 8);  // a bank record
-  s.pcat = s.pnum + align16c(C * P * 8);
-  s.feat = s.pcat + align16c(C * P * 2);
-  s.flat = s.feat + align16c(C * 20);
-  s.total = s.flat + align16c(4 * ((HW + 31) / 32 + 2));
+  s.pcat = s.pnum + align16c(s.pnum_b);
+  s.feat = s.pcat + align16c(s.pcat_b);
+  s.pgrid = s.feat + align16c(s.feat_b);
+  s.cgrid = s.pgrid + align16c(s.pgrid_b);
+  s.flat = s.cgrid + align16c(s.cgrid_b);
+  s.total = s.flat + align16c(4 * ((H * W + 31) / 32 + 2));
   return s;
 }
 
@@ -121,7 +130,8 @@ rollout_pin_kernel(const __grid_constant__ PinRolloutParams p) {
   const uint2* lut = reinterpret_cast<const uint2*>(smem);
   const int H = sh.H(), W = sh.W(), C = sh.C(), HW = H * W, P = sh.P();
   const int max_pins = sh.max_pins();
-  const PinSmem L = pin_smem_layout(C, P, max_pins, HW);
+  const int kind = sh.kind(), K = sh.K(), F = sh.F(), mh = sh.mh(), mw = sh.mw();
+  const PinSmem L = pin_smem_layout(kind, C, P, max_pins, H, W, K, mh, mw);
   uint8_t* es = smem + kLutBytes + (size_t)eic * L.total;
   uint32_t* comps = reinterpret_cast<uint32_t*>(es + L.comps);
   PinRec* pins = reinterpret_cast<PinRec*>(es + L.pins);
@@ -129,6 +139,9 @@ rollout_pin_kernel(const __grid_constant__ PinRolloutParams p) {
   int16_t* inum = reinterpret_cast<int16_t*>(es + L.pnum);
   int16_t* icat = reinterpret_cast<int16_t*>(es + L.pcat);
   float* ifeat = reinterpret_cast<float*>(es + L.feat);
+  uint8_t* ipgrid = es + L.pgrid;    // spatial env: pin_grid (H, W, K)
+  uint8_t* icgrid = es + L.cgrid;    // spatial env: component_grid (C, mh, mw, K)
+  uint8_t* orient = es + L.orient;   // spatial env: orientation each component was placed with
   uint32_t* flat = reinterpret_cast<uint32_t*>(es + L.flat);
   const uint32_t N = (uint32_t)p.n_envs;
   const int pmax = d.mh > d.mw ? d.mh : d.mw;
@@ -156,6 +169,8 @@ rollout_pin_kernel(const __grid_constant__ PinRolloutParams p) {
   for (int q = sl; q < max_pins; q += LPE)
     reinterpret_cast<uint2*>(pins)[q] = reinterpret_cast<const uint2*>(gs + sh.st_pins())[q];
   uint32_t occ = reinterpret_cast<const uint32_t*>(gs + sh.st_occ())[sl];
+  if (kind == 3)
+    for (int c = sl; c < C; c += LPE) orient[c] = gs[sh.st_orient() + c];
   __syncwarp();
 
   // next instance of this env: requested at the start of an episode, consumed at its end
@@ -168,9 +183,10 @@ rollout_pin_kernel(const __grid_constant__ PinRolloutParams p) {
   };
   prefetch(slot);
 
-  // ---- images of the feature tensors (pin:1521-1542, 217-239), rebuilt at a reset ----
-  auto feature_row = [&](int c) {
-    float* row = ifeat + c * 5;
+  // ---- images of the feature tensors (pin:1521-1542, 217-239; spatial:203-239, 1469-1485,
+  // 1663-1697), rebuilt at a reset and updated by every placement ----
+  auto feature_row = [&](int c) {  // [h, w, x|-1, y|-1, h*w/(H*W)]; the spatial env's pin ids stay
+    float* row = ifeat + c * F;
     float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f, f4 = 0.f;
     if (c < n_comp) {
       const uint32_t r = comps[c];
@@ -183,27 +199,68 @@ rollout_pin_kernel(const __grid_constant__ PinRolloutParams p) {
     }
     row[0] = f0; row[1] = f1; row[2] = f2; row[3] = f3; row[4] = f4;
   };
-  auto pin_row = [&](int q) {  // the winner of a (component, pin_id) row writes it
+  auto pin_row = [&](int q) {  // the winner of a feature row writes it (spatial: every pin, row = pin_id)
     const PinRec pr = pins[q];
     if (!(pr.flags & kPinWinner)) return;
     const uint32_t r = comps[pr.comp];
     const int cx = (r >> 16) & 0xff, cy = r >> 24;
     const int ax = cx == 0xFF ? -1 : cx + pr.rx, ay = cx == 0xFF ? -1 : cy + pr.ry;
-    const int row = pr.comp * P + pr.pin_id;
+    const int row = kind == 3 ? (int)pr.pin_id : pr.comp * P + pr.pin_id;
     *reinterpret_cast<uint2*>(inum + row * 4) =
         make_uint2((uint32_t)pr.rx | ((uint32_t)pr.ry << 16), ((uint32_t)ax & 0xffffu) | ((uint32_t)ay << 16));
-    icat[row] = pr.net;
+    if (kind == 3) *reinterpret_cast<uint32_t*>(icat + row * 2) = (uint32_t)pr.net | ((uint32_t)pr.comp << 16);
+    else icat[row] = pr.net;
   };
   // comps / pins final in shared memory (after a __syncwarp); called by the whole warp, the
   // groups with `on` unset only take part in the barriers
   auto rebuild_images = [&](bool on) {
     if (on) {
-      for (int i = sl; i < (L.feat - L.pnum) >> 4; i += LPE) reinterpret_cast<uint4*>(es + L.pnum)[i] = make_uint4(0, 0, 0, 0);
-      for (int c = sl; c < C; c += LPE) feature_row(c);
+      for (int i = sl; i < (L.flat - L.pnum) >> 4; i += LPE) reinterpret_cast<uint4*>(es + L.pnum)[i] = make_uint4(0, 0, 0, 0);
     }
     __syncwarp();
-    if (on)
-      for (int q = sl; q < n_pins; q += LPE) pin_row(q);
+    if (on) {
+      for (int c = sl; c < C; c += LPE) {
+        feature_row(c);
+        if (kind == 3) {  // the pin ids of the component, padded with -1 (rows of absent components stay 0)
+          const float pad = c < n_comp ? -1.f : 0.f;
+          for (int f = 5; f < F; ++f) ifeat[c * F + f] = pad;
+        }
+      }
+      if (kind == 3) {
+        if (sl == 0) { icat[2 * (C * P)] = -1; icat[2 * (C * P) + 1] = -1; }  // the sentinel row
+        // component_grid: channel 0 all ones over the box of every component (spatial:1677-1697)
+        const int cells = mh * mw;
+        for (int i = sl; i < n_comp * cells; i += LPE) icgrid[i * K] = 1;
+        // pin_grid channel 0: occupied cells (all of them; the placed pins clear theirs below)
+        if (sl < H)
+          for (uint32_t b = occ; b; b &= b - 1) ipgrid[(sl * W + (__ffs((int)b) - 1)) * K] = 1;
+      }
+    }
+    __syncwarp();
+    if (on) {
+      for (int q = sl; q < n_pins; q += LPE) {
+        pin_row(q);
+        if (kind == 3) {
+          const PinRec pr = pins[q];
+          ifeat[pr.comp * F + 5 + pr.rank] = (float)pr.pin_id;
+          // component_grid is drawn from the UN-rotated coordinates: undo the placement rotation
+          const uint32_t r = comps[pr.comp];
+          const int ch_ = r & 0xff, cw_ = (r >> 8) & 0xff, oc = orient[pr.comp];
+          int rx = pr.rx, ry = pr.ry;
+          if (oc == 1) { rx = ch_ - 1 - pr.ry; ry = pr.rx; }
+          else if (oc == 2) { rx = ch_ - 1 - pr.rx; ry = cw_ - 1 - pr.ry; }
+          else if (oc == 3) { rx = pr.ry; ry = cw_ - 1 - pr.rx; }
+          icgrid[((pr.comp * mh + rx) * mw + ry) * K + pr.net + 1] = 1;
+          // pin_grid (spatial:1663-1675): a placed pin clears channel 0 of its cell and sets channel net + 1
+          const int cx = (r >> 16) & 0xff, cy = r >> 24;
+          if (cx != 0xFF) {
+            uint8_t* cell = ipgrid + ((cx + pr.rx) * W + cy + pr.ry) * K;
+            cell[0] = 0;
+            cell[pr.net + 1] = 1;
+          }
+        }
+      }
+    }
     __syncwarp();
   };
   rebuild_images(true);
@@ -311,7 +368,12 @@ rollout_pin_kernel(const __grid_constant__ PinRolloutParams p) {
     if (valid && sl >= x && sl < x + ph) occ |= low_mask<uint32_t>(pw) << y;
     __syncwarp();  // every lane has read comps[cur]
     if (valid) {
-      if (sl == 0) comps[cur] = (comps[cur] & 0xffffu) | ((uint32_t)x << 16) | ((uint32_t)y << 24);
+      if (sl == 0) {
+        comps[cur] = (comps[cur] & 0xffffu) | ((uint32_t)x << 16) | ((uint32_t)y << 24);
+        if (kind == 3) orient[cur] = (uint8_t)o;
+      }
+      if (kind == 3 && sl >= x && sl < x + ph)  // pin_grid channel 0 of the new footprint
+        for (int j = y; j < y + pw; ++j) ipgrid[(sl * W + j) * K] = 1;
       if (o != 0) {  // Component.place_component (pin:156-204): the relative coordinates rotate in place
         for (int q = sl; q < n_pins; q += LPE) {
           PinRec pr = pins[q];
@@ -329,8 +391,16 @@ rollout_pin_kernel(const __grid_constant__ PinRolloutParams p) {
     __syncwarp();
     if (valid) {  // the images: one component row, the rows of its pins
       if (sl == 0) feature_row(cur);
-      for (int q = sl; q < n_pins; q += LPE)
-        if (pins[q].comp == cur) pin_row(q);
+      for (int q = sl; q < n_pins; q += LPE) {
+        const PinRec pr = pins[q];
+        if (pr.comp != cur) continue;
+        pin_row(q);
+        if (kind == 3) {
+          uint8_t* cell = ipgrid + ((x + pr.rx) * W + y + pr.ry) * K;
+          cell[0] = 0;
+          cell[pr.net + 1] = 1;
+        }
+      }
       cur += 1;
     }
     ep_len += 1;
@@ -409,6 +479,8 @@ rollout_pin_kernel(const __grid_constant__ PinRolloutParams p) {
         const uint2* rp = reinterpret_cast<const uint2*>(nrec + sh.rec_pins());
         for (int c = sl; c < C; c += LPE) comps[c] = rc[c];
         for (int q = sl; q < max_pins; q += LPE) reinterpret_cast<uint2*>(pins)[q] = rp[q];
+        if (kind == 3)
+          for (int c = sl; c < C; c += LPE) orient[c] = 0;
       }
       __syncwarp();
       if (restart) prefetch(slot);
@@ -434,9 +506,13 @@ rollout_pin_kernel(const __grid_constant__ PinRolloutParams p) {
       write_board_g<LPE, S>(sh, mk, m0, flat, sl, live, lut, 2 * HW);
       write_board_g<LPE, S>(sh, mk + HW, m1, flat, sl, live, lut, 2 * HW);
     }
-    copy_out_g<LPE>(p.base.feat + (size_t)se * (uint32_t)(C * 5), ifeat, C * 20, sl, live);
-    copy_out_g<LPE>(p.base.pnum + (size_t)se * (uint32_t)(C * P * 4), inum, C * P * 8, sl, live);
-    copy_out_g<LPE>(p.base.pcat + (size_t)se * (uint32_t)(C * P), icat, C * P * 2, sl, live);
+    copy_out_g<LPE>(p.base.feat + (size_t)se * (uint32_t)(C * F), ifeat, L.feat_b, sl, live);
+    copy_out_g<LPE>(p.base.pnum + (size_t)se * (uint32_t)(L.pnum_b >> 1), inum, L.pnum_b, sl, live);
+    copy_out_g<LPE>(p.base.pcat + (size_t)se * (uint32_t)(L.pcat_b >> 1), icat, L.pcat_b, sl, live);
+    if (kind == 3) {
+      copy_out_g<LPE>(p.base.pgrid + (size_t)se * (uint32_t)L.pgrid_b, ipgrid, L.pgrid_b, sl, live);
+      copy_out_g<LPE>(p.base.cgrid + (size_t)se * (uint32_t)L.cgrid_b, icgrid, L.cgrid_b, sl, live);
+    }
     if (live) {
       uint8_t* pm = p.base.place_mask + (size_t)se * (uint32_t)C;
       for (int c = sl; c < C; c += LPE)  // pin:1577-1579, 1649-1657
@@ -461,6 +537,8 @@ rollout_pin_kernel(const __grid_constant__ PinRolloutParams p) {
   for (int q = sl; q < max_pins; q += LPE)
     reinterpret_cast<uint2*>(gs + sh.st_pins())[q] = reinterpret_cast<const uint2*>(pins)[q];
   reinterpret_cast<uint32_t*>(gs + sh.st_occ())[sl] = occ;
+  if (kind == 3)
+    for (int c = sl; c < C; c += LPE) gs[sh.st_orient() + c] = orient[c];
 }
 
 // Terminal rewards of the routing jobs one launch of rollout_pin_kernel left (find_reward,

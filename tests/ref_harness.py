@@ -172,5 +172,6 @@ from fuzz_configs import FUZZ  # noqa: E402
 CONFIGS.update(FUZZ)
 # centroid-reward twins of ragged pin configurations: the multi-step pin kernel
 # (pcb_pin_small.cuh) with runtime shapes and 8 / 16 / 32 lanes per env
-for _k in ("S_pin", "FZ_rect_pin_0", "FZ_rect_pin_3", "FZ_rect_pin_4", "FZ_rect_pin_6"):
+for _k in ("S_pin", "S_spa", "FZ_rect_pin_0", "FZ_rect_pin_3", "FZ_rect_pin_4", "FZ_rect_pin_6",
+           "FZ_rect_spatial_pin_4"):
     CONFIGS[_k + "_cen"] = dict(CONFIGS[_k], reward_type="centroid")

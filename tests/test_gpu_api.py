@@ -157,8 +157,8 @@ def test_reference_dtype_mode_equals_the_oracle_value_for_value(name):
     env.close()
 
 
-def test_fused_rollout_is_refused_for_beam_rewards_spatial_and_wide_boards():
-    for name in ("C_both", "D", "S_wide_pin", "S_wide_sq", "S_wide_rect"):
+def test_fused_rollout_is_refused_for_beam_rewards_and_wide_boards():
+    for name in ("C_both", "D_both", "S_wide_pin", "S_wide_spa", "S_wide_sq", "S_wide_rect"):
         env = make(name, 8)
         assert not env.fused_rollout(True)
         env.close()
@@ -576,14 +576,16 @@ def _graph_rollout_body(name, n, a, b):
 
 
 @pytest.mark.parametrize("name", ["C", "REF_pin", "S_pin_tight", "S_pin_cen", "FZ_rect_pin_0_cen",
-                                  "FZ_rect_pin_3_cen", "FZ_rect_pin_4_cen", "FZ_rect_pin_6_cen"])
+                                  "FZ_rect_pin_3_cen", "FZ_rect_pin_4_cen", "FZ_rect_pin_6_cen",
+                                  "D", "REF_spatial", "S_spa_tight", "S_spa_cen", "FZ_rect_spatial_pin_4_cen"])
 @pytest.mark.parametrize("autoreset", [True, False])
 def test_pin_fused_rollout_equals_per_step(name, autoreset):
     """rollout_pin_kernel (many steps per launch, 32/LPE envs per warp, rewards from a job list
     afterwards) against the per-step kernels: every observation slice, the logged actions,
     rewards and dones of every step, the state records, the result tensors and the statistics."""
     cfg = CONFIGS[name]
-    if cfg["type"] != "rectangle_pin" or cfg["reward_type"] != "centroid" or max(cfg["height"], cfg["width"]) > 32:
+    if cfg["type"] not in ("rectangle_pin", "rectangle_spatial_pin") or cfg["reward_type"] != "centroid" or max(
+            cfg["height"], cfg["width"]) > 32:
         pytest.skip("not a configuration of the fused pin kernel")
     n, T = 203, 41
     a = make(name, n, seed=11, obs_ring=T + 1, bank_size=5 * n, autoreset=autoreset)

@@ -35,7 +35,7 @@ def test_no_store_leaves_its_buffer(guarded, name):
                                    bank_size=2 * n, force_generic=generic)
             env.reset()
             env.rollout_random(23, seed=1)
-            if env.kind == "rectangle_pin":   # both rollout paths of the pin env
+            if env.kind in ("rectangle_pin", "rectangle_spatial_pin"):   # both rollout paths of the pin envs
                 env.fused_rollout(False)
                 env.rollout_random(9, seed=6)
                 env.fused_rollout(True)
