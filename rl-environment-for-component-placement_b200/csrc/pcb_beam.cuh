@@ -240,27 +240,75 @@ __device__ __forceinline__ void beam_route_net(const JobPin* pins, int lo, int m
 // Beam routes of all finished episodes of a step: ONE THREAD PER (job, net), so a warp
 // routes 32 independent nets (the router is serial per net).  The paths are written into
 // the job records; reward_kernel<true> picks them up.
+// The cost of a net grows steeply with its pin count (2 pins: a few hundred instructions, 6
+// pins: several thousand), and consecutive (job, net) items have unrelated sizes, so a warp
+// would run every lane's longest path.  Each CTA therefore counting-sorts its 128 items by
+// pin count in shared memory first: the lanes of a warp then route nets of (almost) the same
+// size.  The order of the items does not change any result.
+#ifndef PCB_BEAM_SORT
+#define PCB_BEAM_SORT 1
+#endif
 __global__ void __launch_bounds__(128) beam_kernel(const __grid_constant__ Params p) {
   const Dims& d = p.d;
   const int nets_max = d.K - 1;
   const uint32_t count = p.job_count[p.step_no & 3];
   const uint32_t total = count * (uint32_t)nets_max;
   const int stride = job_stride(d.max_pins, d.K);
-  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const uint32_t j = idx / (uint32_t)nets_max;
-    const int net = (int)(idx - j * (uint32_t)nets_max);
-    uint8_t* job = p.jobs + (size_t)j * stride;
-    const RouteJob* hdr = reinterpret_cast<const RouteJob*>(job);
-    const int n_pins = hdr->n_pins;
-    if (net >= hdr->n_nets) continue;
-    const JobPin* pins = reinterpret_cast<const JobPin*>(job + 32);
-    int lo = 0;
-    while (lo < n_pins && pins[lo].net != net) ++lo;  // pins are net-major
-    int hi = lo;
-    while (hi < n_pins && pins[hi].net == net) ++hi;
-    uint16_t* nxt = reinterpret_cast<uint16_t*>(job + job_path_offset(d.max_pins));
-    uint16_t* start = nxt + d.max_pins;
-    beam_route_net(pins, lo, hi - lo, d.beam_width, d.norm_fma, nxt, start + net);
+  __shared__ uint32_t s_bin[32];
+  __shared__ uint32_t s_item[128];
+  const int tid = threadIdx.x;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {  // CTA-uniform
+    uint32_t idx = base + tid;
+    int lo = 0, m = 0;
+    if (idx < total) {
+      const uint32_t j = idx / (uint32_t)nets_max;
+      const int net = (int)(idx - j * (uint32_t)nets_max);
+      const uint8_t* job = p.jobs + (size_t)j * stride;
+      const RouteJob* hdr = reinterpret_cast<const RouteJob*>(job);
+      const int n_pins = hdr->n_pins;
+      if (net < hdr->n_nets) {
+        const JobPin* pins = reinterpret_cast<const JobPin*>(job + 32);
+        while (lo < n_pins && pins[lo].net != net) ++lo;  // pins are net-major
+        int hi = lo;
+        while (hi < n_pins && pins[hi].net == net) ++hi;
+        m = hi - lo;
+      }
+    }
+#if PCB_BEAM_SORT
+    // counting sort of the CTA's items by pin count, largest first
+    if (tid < 32) s_bin[tid] = 0u;
+    __syncthreads();
+    const int key = 31 - (m < 31 ? m : 31);
+    const uint32_t rank = atomicAdd(&s_bin[key], 1u);
+    __syncthreads();
+    if (tid < 32) {
+      const uint32_t c = s_bin[tid];
+      uint32_t incl = c;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t v = __shfl_up_sync(kFull, incl, off);
+        if (tid >= off) incl += v;
+      }
+      s_bin[tid] = incl - c;  // first position of the bin
+    }
+    __syncthreads();
+    s_item[s_bin[key] + rank] = (uint32_t)tid | ((uint32_t)lo << 8) | ((uint32_t)m << 20);
+    __syncthreads();
+    const uint32_t it = s_item[tid];
+    idx = base + (it & 0xffu);
+    lo = (int)((it >> 8) & 0xfffu);
+    m = (int)(it >> 20);
+    __syncthreads();  // s_bin / s_item are reused by the next round
+#endif
+    if (m > 0) {
+      const uint32_t j = idx / (uint32_t)nets_max;
+      const int net = (int)(idx - j * (uint32_t)nets_max);
+      uint8_t* job = p.jobs + (size_t)j * stride;
+      const JobPin* pins = reinterpret_cast<const JobPin*>(job + 32);
+      uint16_t* nxt = reinterpret_cast<uint16_t*>(job + job_path_offset(d.max_pins));
+      uint16_t* start = nxt + d.max_pins;
+      beam_route_net(pins, lo, m, d.beam_width, d.norm_fma, nxt, start + net);
+    }
   }
 }
 
