@@ -119,7 +119,7 @@ struct pcb_env {
   bool overlap;          // pcb_rollout_random overlaps the reward kernel with the next step
   int sms;               // multiprocessors of the device
   bool fused;            // pcb_rollout_random uses rollout_small_kernel (pin-less kinds, H, W <= 32)
-  // pin env, centroid reward, H, W <= 32: rollout_pin_kernel (pcb_pin_small.cuh) -- many steps
+  // pin / pin-spatial env, H, W <= 32: rollout_pin_kernel (pcb_pin_small.cuh) -- many steps
   // per launch, 32/LPE envs per warp, terminal rewards from a job list afterwards
   bool fused_pin, fused_pin_ok;
   size_t pin_smem;       // dynamic shared memory per CTA (4 warps)
@@ -667,7 +667,7 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
     memset(&none, 0, sizeof none);
     TRY(small_dispatch(e, true, nullptr, none));
   }
-  if (d.kind >= 2 && !e->wide && d.reward_type == PCB_REWARD_CENTROID && cfg->reserved0 != 1) {
+  if (d.kind >= 2 && !e->wide && cfg->reserved0 != 1) {
     // Small boards pack several envs into a warp; a small batch of any board is launch- and
     // latency-bound with one launch per step.  A large batch of a 32-row board keeps the
     // per-step kernels (one warp per env either way, and the reward kernel overlaps the next
@@ -677,6 +677,11 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
     // per-step, 12 288 envs 6.4e8 against 6.3e8, 16 384 envs 6.2e8 against 6.7e8
     // spatial env (D): 4 096 envs 2.8e8 against 2.1e8, 8 192 envs 2.7e8 against 3.0e8
     int max_envs = d.kind == 3 ? 6144 : 12288;
+    // reward types beam / both: always.  Per step their router + reward kernels are the critical
+    // path (one side stream, ~100 us of latency-bound work per step); over the job list of a
+    // 64-step launch the same kernels run with 64x the parallelism: C "both" at 65 536 envs
+    // 4.0e8 -> 5.5e8 env-steps/s, "beam" 4.6e8 -> 6.0e8, at 4 096 envs 7.5e7 -> 4.6e8.
+    if (d.reward_type != PCB_REWARD_CENTROID) max_envs = 0x7fffffff;
     if (const char* f = getenv("PCB_PIN_FUSED_MAX_ENVS")) max_envs = atoi(f);
     e->fused_pin_ok = true;
     e->fused_pin = lpe < 32 || num_envs <= max_envs;
@@ -696,7 +701,8 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
     e->reward_smem = (size_t)((route_scratch_bytes(d.max_pins, d.K) + 15) & ~15) * kWarpsPerCta;
     TRY(set_smem(reward_kernel<false>, e->reward_smem));
     TRY(set_smem(reward_kernel<true>, e->reward_smem));
-    TRY(set_smem(reward_list_kernel, e->reward_smem));
+    TRY(set_smem(reward_list_kernel<false>, e->reward_smem));
+    TRY(set_smem(reward_list_kernel<true>, e->reward_smem));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     int want = (num_envs + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -1267,16 +1273,27 @@ static int rollout_pin_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* 
     r.final_from = std::max(0, n_steps - 2 - t0);  // beyond nt when the call goes on after this launch
     const int want_ctas = (int)std::min<size_t>(((size_t)nt * N + kWarpsPerCta - 1) / kWarpsPerCta,
                                                 (size_t)e->sms * PCB_REWARD_GRID_MULT);
+    cudaStream_t rst = overlap ? e->side : st;
     if (overlap) {
       CU(cudaEventRecord(e->ev_step[buf], st));
       CU(cudaStreamWaitEvent(e->side, e->ev_step[buf], 0));
-      reward_list_kernel<<<std::max(1, want_ctas), kWarpsPerCta * 32, e->reward_smem, e->side>>>(r);
+    }
+    if (e->d.reward_type == PCB_REWARD_CENTROID) {
+      reward_list_kernel<false><<<std::max(1, want_ctas), kWarpsPerCta * 32, e->reward_smem, rst>>>(r);
+    } else {
+      // beam_kernel over the list: it reads its job count at job_count[step_no & 3]
+      Params bp;
+      memset(&bp, 0, sizeof bp);
+      bp.d = e->d; bp.jobs = e->pin_jobs[buf]; bp.job_count = e->pin_job_total[buf]; bp.step_no = 0;
+      beam_kernel<<<std::max(1, want_ctas), 128, 0, rst>>>(bp);
       CU(cudaGetLastError());
+      e->launches += 1;
+      reward_list_kernel<true><<<std::max(1, want_ctas), kWarpsPerCta * 32, e->reward_smem, rst>>>(r);
+    }
+    CU(cudaGetLastError());
+    if (overlap) {
       CU(cudaEventRecord(e->ev_rew[buf], e->side));
       e->rew_pending[buf] = true;
-    } else {
-      reward_list_kernel<<<std::max(1, want_ctas), kWarpsPerCta * 32, e->reward_smem, st>>>(r);
-      CU(cudaGetLastError());
     }
     e->launches += 2;
     e->slice = (e->slice + nt) % e->ring;

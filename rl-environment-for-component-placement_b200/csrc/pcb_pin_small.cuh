@@ -559,6 +559,7 @@ struct RewardListParams {
   double* stats;
 };
 
+template <bool BEAM>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, PCB_REWARD_MIN_BLOCKS)
 reward_list_kernel(const __grid_constant__ RewardListParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -579,7 +580,21 @@ reward_list_kernel(const __grid_constant__ RewardListParams p) {
     route_prepare(reinterpret_cast<const JobPin*>(job + 32), rs, lane, n_pins, n_nets);
     int crossings = 0;
     double length = 0.0;
-    centroid_route(d, rs, lane, n_pins, crossings, length);
+    if (!BEAM || d.reward_type == 0) {
+      centroid_route(d, rs, lane, n_pins, crossings, length);
+    } else if constexpr (BEAM) {
+      // the paths were routed by beam_kernel (one thread per net) into the job record
+      const uint16_t* jn = reinterpret_cast<const uint16_t*>(job + job_path_offset(d.max_pins));
+      for (int q = lane; q < n_pins; q += 32) rs.nxt[q] = jn[q];
+      for (int k = lane; k < n_nets; k += 32) rs.start[k] = jn[d.max_pins + k];
+      __syncwarp();
+      beam_route(d, rs, lane, n_pins, n_nets, crossings, length);
+      if (d.reward_type == 2) {  // "both": fewer crossings wins, beam on ties (pin:643-661)
+        int c2; double l2;
+        centroid_route(d, rs, lane, n_pins, c2, l2);
+        if (c2 < crossings) { crossings = c2; length = l2; }
+      }
+    }
     const double wl = length / d.wl_norm;
     const double ni = (double)crossings / d.ni_norm;
     const double reward = -1.0 * (d.ww * wl + d.wi * ni);

@@ -77,7 +77,8 @@ def test_reference_shipped_configs(name):
 
 @pytest.mark.parametrize("name", ["C", "REF_pin", "S_pin_tight", "S_pin_cen", "FZ_rect_pin_0_cen",
                                   "FZ_rect_pin_3_cen", "FZ_rect_pin_4_cen", "FZ_rect_pin_6_cen",
-                                  "D", "REF_spatial", "S_spa_tight", "S_spa_cen", "FZ_rect_spatial_pin_4_cen"])
+                                  "D", "REF_spatial", "S_spa_tight", "S_spa_cen", "C_both", "C_beam", "S_pin",
+                                  "S_pin_beam3", "S_spa", "FZ_rect_pin_0", "FZ_rect_pin_3", "FZ_rect_pin_6"])
 def test_pin_rollout_kernel_against_oracle(name):
     """pcb_rollout_random of the pin env in its multi-step kernel (pcb_pin_small.cuh: 8 / 16 / 32
     lanes per env, compile-time and runtime shapes): the logged actions replayed through the
