@@ -86,6 +86,12 @@ struct pcb_env {
   double* stats;
   int32_t* d_actions;  // staging for pcb_step_host / ping-pong of pcb_rollout_random
   int32_t* d_actions2;
+  // the last step of a pcb_rollout_random call also draws the actions of the step after it;
+  // the next call with the same seed on the same stream starts from them instead of
+  // launching the stand-alone sampler (cleared by everything else that moves the state)
+  int32_t* pend_actions;
+  uint64_t pend_seed, pend_step;
+  cudaStream_t pend_stream;
   // reward and done of one step sit side by side ([reward f64 x N | done u8 x N], one block
   // per result half) so that pcb_step_host brings both back with ONE device-to-host copy
   size_t res_stride;   // bytes between the two halves
@@ -614,6 +620,7 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
     e->guard = g && g[0] == '1';
   }
   e->ratio_lut = nullptr; e->d_actions = nullptr; e->d_actions2 = nullptr;
+  e->pend_actions = nullptr; e->pend_seed = 0; e->pend_step = 0; e->pend_stream = nullptr;
   e->res_stride = 0; e->hs_actions = nullptr; e->hs_reward = nullptr; e->hs_done = nullptr;
   e->hs_steps = 0; e->copy = nullptr; e->ev_host = nullptr;
   e->use_graph = true; e->graph = nullptr; e->graph_len = 0; e->graph_slice = 0; e->graph_step0 = 0;
@@ -927,6 +934,7 @@ int pcb_reset(pcb_env_t* e, const uint8_t* d_reset_mask, void* stream) {
   if (rc) return rc;
   CU(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream;
+  e->pend_actions = nullptr;
   if (!d_reset_mask) {
     e->slice = 0;
     e->step_no = 0;
@@ -959,6 +967,7 @@ static int step_impl(pcb_env_t* e, const int32_t* d_actions, int action_format, 
     return fail(PCB_ERR_INVALID, "unknown action format %d", action_format);
   CU(cudaSetDevice(e->device));
   cudaStream_t st = (cudaStream_t)stream;
+  e->pend_actions = nullptr;
   if (e->fused && !d_next_actions)  // pin-less kinds: the multi-env-per-warp kernel, one step
     return rollout_fused(e, seed, 1, nullptr, reward_row, done_row, st, d_actions, action_format);
   const bool routes = e->d.kind >= 2;
@@ -1151,6 +1160,7 @@ int pcb_set_state(pcb_env_t* e, const void* h_state, uint64_t step_no, void* str
   if (e->job_count) CU(cudaMemsetAsync(e->job_count, 0, 4 * sizeof(uint32_t), st));
   CU(cudaStreamSynchronize(st));
   e->step_no = step_no;
+  e->pend_actions = nullptr;
   return 0;
 }
 
@@ -1323,10 +1333,19 @@ static int gcd_i(int a, int b) { return b ? gcd_i(b, a % b) : a; }
 // moving -- the step counter of the random policy -- is read from device memory
 // (Params::step_base = steps since capture), set before a run of replays and advanced by the
 // last node of the graph.
-static int graph_length(const pcb_env_t* e) {
+// Every replay ends with the join of its last reward kernel (nothing overlaps it), so a
+// graph is as long as the call allows, between ~16 and ~64 steps; a captured graph that
+// still fits is kept (capturing costs milliseconds), so the length only ever shrinks.
+#ifndef PCB_GRAPH_MAX_STEPS
+#define PCB_GRAPH_MAX_STEPS 64
+#endif
+static int graph_length(const pcb_env_t* e, int n_steps) {
   const int base = e->ring * 4 / gcd_i(e->ring, 4);  // lcm(ring, 4)
   if (base > 128) return 0;
-  return base * std::max(1, 16 / base);              // at least ~16 steps per launch
+  const int lo = base * std::max(1, 16 / base), hi = base * std::max(1, PCB_GRAPH_MAX_STEPS / base);
+  if (n_steps < lo) return 0;
+  if (e->graph && e->graph_len >= lo && e->graph_len <= n_steps) return e->graph_len;
+  return std::min(hi, n_steps / base * base);
 }
 
 static bool graph_allowed(pcb_env_t* e, cudaStream_t st) {
@@ -1439,7 +1458,7 @@ int pcb_rollout_random_logged(pcb_env_t* e, uint64_t seed, int n_steps, int32_t*
   const int total_steps = n_steps;
   // CUDA-graph plan: `dlt` plain steps walk the handle into the phase the graph was captured
   // in (or a graph is captured right here, dlt = 0), then replays, then the remainder
-  const int L = graph_length(e);
+  const int L = graph_length(e, n_steps);
   const bool overlap = e->overlap && e->d.kind >= 2;
   bool graphed = !d_actions_log && !d_reward_log && !d_done_log && L > 0 && n_steps >= L && graph_allowed(e, st);
   bool capture = false;
@@ -1455,8 +1474,15 @@ int pcb_rollout_random_logged(pcb_env_t* e, uint64_t seed, int n_steps, int32_t*
   // draws the action of the following step (same counter as the sampler would use).  The two
   // action buffers ping-pong; a replay expects its first actions in d_actions.
   int32_t* cur = d_actions_log ? d_actions_log : ((graphed && (dlt & 1)) ? e->d_actions2 : e->d_actions);
-  rc = pcb_sample_random_actions(e, seed, cur, stream);
-  if (rc) return rc;
+  if (e->pend_actions && e->pend_seed == seed && e->pend_step == e->step_no && e->pend_stream == st) {
+    // the previous call's last step already drew them
+    if (e->pend_actions != cur)
+      CU(cudaMemcpyAsync(cur, e->pend_actions, per * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  } else {
+    rc = pcb_sample_random_actions(e, seed, cur, stream);
+    if (rc) return rc;
+  }
+  e->pend_actions = nullptr;
   // plain per-step launches; `cur` holds the actions of the next step throughout
   auto plain = [&](int count, bool last_of_call) -> int {
     for (int t = 0; t < count; ++t) {
@@ -1465,6 +1491,8 @@ int pcb_rollout_random_logged(pcb_env_t* e, uint64_t seed, int n_steps, int32_t*
       if (!(last_of_call && t + 1 == count))
         nxt = d_actions_log ? d_actions_log + (size_t)(done + 1) * per
                             : (cur == e->d_actions ? e->d_actions2 : e->d_actions);
+      else  // the actions of the step after this call: kept for the next call
+        nxt = cur == e->d_actions ? e->d_actions2 : e->d_actions;
       int rc2 = step_impl(e, cur, PCB_ACTION_TUPLE, seed, nxt, stream, e->overlap,
                           d_reward_log ? d_reward_log + (size_t)done * N : nullptr,
                           d_done_log ? d_done_log + (size_t)done * N : nullptr);
@@ -1488,7 +1516,10 @@ int pcb_rollout_random_logged(pcb_env_t* e, uint64_t seed, int n_steps, int32_t*
   if (rc) return rc;
   rc = join_rewards(e, (cudaStream_t)stream);
   if (rc) return rc;
-  return restore_result_halves(e, total_steps, d_reward_log, d_done_log, (cudaStream_t)stream);
+  rc = restore_result_halves(e, total_steps, d_reward_log, d_done_log, (cudaStream_t)stream);
+  // (a call that ends on a replay leaves them in d_actions, like the last plain step)
+  e->pend_actions = cur; e->pend_seed = seed; e->pend_step = e->step_no; e->pend_stream = st;
+  return rc;
 }
 
 // the result tensors ([2] halves by step parity) describe the last two steps: copy them back

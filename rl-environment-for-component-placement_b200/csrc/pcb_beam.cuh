@@ -322,13 +322,14 @@ __device__ __forceinline__ void beam_route(const Dims& d, const RouteScratch& rs
     if (nx != 0xFFFF) {
       const double x1 = (double)rs.px[q], y1 = (double)rs.py[q];
       x2 = (double)rs.px[nx]; y2 = (double)rs.py[nx];
-      box = make_box(x1, y1, x2, y2);
+      put_segment(rs, q, rs.px[q], rs.py[q], rs.px[nx], rs.py[nx], 1);
+      box = make_box((int)rs.px[q], (int)rs.py[q], (int)rs.px[nx], (int)rs.py[nx]);
       len = norm2(x1 - x2, y1 - y2, d.norm_fma);
     }
     rs.x2[q] = x2; rs.y2[q] = y2; rs.box[q] = box; rs.dist[q] = len;
   }
   __syncwarp();
-  crossings = count_crossings(rs, lane, n_pins);
+  crossings = count_crossings(rs, lane, n_pins, n_nets);
   // find_wirelength: nets in order, segments in path order, sequential float64 sum
   double acc = 0.0;
   if (lane == 0) {

@@ -18,6 +18,7 @@
 #include <stdint.h>
 
 #include "pcb_layout.h"
+#include "pcb_cross.h"
 
 namespace pcb {
 
@@ -1017,13 +1018,17 @@ struct RouteScratch {
   double* cx;         // [K] centroid per net
   double* cy;
   uint2* box;         // [max_pins] (lo, guarded hi)
-  uint32_t* queue;    // [kPairQueue] candidate pairs (s << 16 | t)
+  uint2* seg;         // [max_pins] integer endpoints times scale: x = ax | ay << 16, y = bx | by << 16
+  uint32_t* queue;    // [kPairQueue] candidate pairs (s << 16 | t) whose boxes touch
+  uint32_t* hqueue;   // [kPairQueue] pairs the integer test leaves to the float64 formula
+  int* nsum;          // [2 K] coordinate sums of each net (x, y)
   int16_t* px;
   int16_t* py;
   uint16_t* nxt;      // beam route: next pin on the path, 0xFFFF = path end
   uint16_t* net_off;  // [K + 1] first pin of each net (pins are net-major)
   uint16_t* start;    // [K] beam route: first pin of the path
   uint8_t* net;       // [max_pins] net of pin q
+  uint8_t* scale;     // [max_pins] scale byte of seg[q] (pcb_cross.h)
 };
 
 __device__ __forceinline__ RouteScratch route_scratch(uint8_t* scr, int max_pins, int K) {
@@ -1035,21 +1040,35 @@ __device__ __forceinline__ RouteScratch route_scratch(uint8_t* scr, int max_pins
   r.cx = reinterpret_cast<double*>(q); q += K * 8;
   r.cy = reinterpret_cast<double*>(q); q += K * 8;
   r.box = reinterpret_cast<uint2*>(q); q += max_pins * 8;
+  r.seg = reinterpret_cast<uint2*>(q); q += max_pins * 8;
   r.queue = reinterpret_cast<uint32_t*>(q); q += kPairQueue * 4;
+  r.hqueue = reinterpret_cast<uint32_t*>(q); q += kPairQueue * 4;
+  r.nsum = reinterpret_cast<int*>(q); q += K * 8;
   r.px = reinterpret_cast<int16_t*>(q); q += max_pins * 2;
   r.py = reinterpret_cast<int16_t*>(q); q += max_pins * 2;
   r.nxt = reinterpret_cast<uint16_t*>(q); q += max_pins * 2;
   r.net_off = reinterpret_cast<uint16_t*>(q); q += (K + 1) * 2;
   r.start = reinterpret_cast<uint16_t*>(q); q += K * 2;
-  r.net = q;
+  r.net = q; q += max_pins;
+  r.scale = q;
   return r;
 }
 
-__device__ __forceinline__ uint2 make_box(double xa, double ya, double xb, double yb) {
-  int x0 = (int)floor(fmin(xa, xb)), x1 = (int)ceil(fmax(xa, xb));
-  int y0 = (int)floor(fmin(ya, yb)), y1 = (int)ceil(fmax(ya, yb));
+__device__ __forceinline__ uint2 pack_box(int x0, int y0, int x1, int y1) {
   return make_uint2((uint32_t)x0 | ((uint32_t)y0 << 16),
                     ((uint32_t)x1 | ((uint32_t)y1 << 16)) | kBoxGuard);
+}
+// pin -> pin segment
+__device__ __forceinline__ uint2 make_box(int xa, int ya, int xb, int yb) {
+  return pack_box(min(xa, xb), min(ya, yb), max(xa, xb), max(ya, yb));
+}
+// pin -> centroid segment.  The box only has to contain the segment: rounding the centroid
+// (a multiple of 1 / pins, pins <= 512, below 64) to float moves it by < 4e-6, which cannot
+// carry it across an integer it is not equal to.
+__device__ __forceinline__ uint2 make_box(int xa, int ya, double cx, double cy) {
+  const float fx = (float)cx, fy = (float)cy;
+  return pack_box(min(xa, __float2int_rd(fx)), min(ya, __float2int_rd(fy)),
+                  max(xa, __float2int_ru(fx)), max(ya, __float2int_ru(fy)));
 }
 __device__ __forceinline__ uint2 no_box() { return make_uint2(kNoBoxLo, kBoxGuard); }
 
@@ -1077,15 +1096,40 @@ __device__ __forceinline__ void route_prepare(const JobPin* pins, const RouteScr
     for (int q = lo; q < hi; ++q) { sx += rs.px[q]; sy += rs.py[q]; }
     rs.cx[net] = (double)sx / (double)(hi - lo);
     rs.cy[net] = (double)sy / (double)(hi - lo);
+    rs.nsum[2 * net] = sx;
+    rs.nsum[2 * net + 1] = sy;
   }
   __syncwarp();
 }
 
-// find_num_intersection (pin:663-685) over the per-pin segment arrays.  Lane t owns
-// segment t and walks the segments s of earlier nets; pairs whose integer boxes do
-// not touch cannot intersect (the reference requires the point inside both boxes),
-// the others are queued and tested 32 at a time with the reference's float64 formula.
-__device__ __forceinline__ int count_crossings(const RouteScratch& rs, int lane, int n_pins) {
+#ifndef PCB_CROSS_INT
+#define PCB_CROSS_INT 1   // 0 = round-1 crossing count (box filter, then float64 for every survivor)
+#endif
+
+// Integer record of the segment headed by pin q (pcb_cross.h): both end points multiplied by
+// `scale`; nets of more than kMaxExactScale pins get scale byte 0 and their pairs go to the
+// float64 formula directly.
+__device__ __forceinline__ void put_segment(const RouteScratch& rs, int q, int ax, int ay, int bx,
+                                            int by, int scale) {
+  rs.seg[q] = make_uint2((uint32_t)ax | ((uint32_t)ay << 16), (uint32_t)bx | ((uint32_t)by << 16));
+  rs.scale[q] = (uint8_t)segment_scale_byte(scale);
+}
+
+__device__ __forceinline__ int segments_cross_int(const RouteScratch& rs, uint32_t pr) {
+  const int s = pr >> 16, t = pr & 0xffffu;
+  const uint2 S = rs.seg[s], T = rs.seg[t];
+  return segments_cross_int((int)(S.x & 0xffffu), (int)(S.x >> 16), (int)(S.y & 0xffffu),
+                            (int)(S.y >> 16), rs.scale[s], (int)(T.x & 0xffffu), (int)(T.x >> 16),
+                            (int)(T.y & 0xffffu), (int)(T.y >> 16), rs.scale[t]);
+}
+
+// find_num_intersection (pin:663-685) over the per-pin segment arrays: every pair of
+// segments of different nets.  Pairs whose integer boxes do not touch cannot intersect (the
+// reference requires the point inside both boxes); the others are queued, decided 32 at a
+// time by the exact integer test, and what that leaves undecided is queued again for the
+// reference's float64 formula.
+__device__ __forceinline__ int count_crossings(const RouteScratch& rs, int lane, int n_pins,
+                                               int n_nets) {
   int cnt = 0, qn = 0;
   auto heavy = [&](uint32_t pr) -> int {
     int s = pr >> 16, t = pr & 0xffffu;
@@ -1095,6 +1139,62 @@ __device__ __forceinline__ int count_crossings(const RouteScratch& rs, int lane,
     return segments_cross((double)rs.px[s], (double)rs.py[s], rs.x2[s], rs.y2[s],
                           (double)rs.px[t], (double)rs.py[t], rs.x2[t], rs.y2[t]) ? 1 : 0;
   };
+#if PCB_CROSS_INT
+  int hn = 0;
+  const unsigned below = (1u << lane) - 1u;
+  // the first n (<= 32) entries of queue[qn ...): integer test, undecided pairs to hqueue
+  auto decide = [&](int n) {
+    uint32_t pr = 0;
+    int r = 0;
+    if (lane < n) {
+      pr = rs.queue[qn + lane];
+      r = segments_cross_int(rs, pr);
+    }
+    cnt += r & 1;
+    const unsigned hb = __ballot_sync(kFull, r == 2);
+    if (hb != 0) {
+      if (r == 2) rs.hqueue[hn + __popc(hb & below)] = pr;
+      hn += __popc(hb);
+      __syncwarp();
+      if (hn >= 32) {
+        hn -= 32;
+        cnt += heavy(rs.hqueue[hn + lane]);
+        __syncwarp();
+      }
+    }
+  };
+  // net b against every segment of the nets before it: pair i = (s, t) = (i % first, first + i / first)
+  for (int b = 1; b < n_nets; ++b) {
+    const int first = rs.net_off[b], total = first * (rs.net_off[b + 1] - first);
+    // i / first through a reciprocal good to 2 ulp: (i + 0.5) / first is at least 1 / 1024 away
+    // from an integer (first <= 512) and the product is off by less than 512 * 2^-21
+    const float inv = __fdividef(1.0f, (float)first);
+    for (int i0 = 0; i0 < total; i0 += 32) {
+      const int i = min(i0 + lane, total - 1);  // lanes past the end repeat the last pair (loads stay in range)
+      const int q = __float2int_rz(((float)i + 0.5f) * inv);
+      const int s = i - q * first, t = first + q;
+      const bool pass = boxes_touch(rs.box[t], rs.box[s]) && i0 + lane < total;
+      const unsigned pb = __ballot_sync(kFull, pass);
+      if (pb == 0) continue;
+      if (pass) rs.queue[qn + __popc(pb & below)] = ((uint32_t)s << 16) | (uint32_t)t;
+      qn += __popc(pb);
+      __syncwarp();
+      if (qn >= 32) {
+        qn -= 32;
+        decide(32);
+        __syncwarp();
+      }
+    }
+  }
+  if (qn > 0) {
+    const int n = qn;
+    qn = 0;
+    decide(n);
+  }
+  if (lane < hn) cnt += heavy(rs.hqueue[lane]);
+  __syncwarp();
+  return __reduce_add_sync(kFull, cnt);
+#else
   for (int t0 = 0; t0 < n_pins; t0 += 32) {
     const int t = t0 + lane;
     uint2 mine = no_box();
@@ -1123,22 +1223,34 @@ __device__ __forceinline__ int count_crossings(const RouteScratch& rs, int lane,
   if (lane < qn) cnt += heavy(rs.queue[lane]);
   __syncwarp();
   return __reduce_add_sync(kFull, cnt);
+#endif
 }
 
 // Centroid route (route_pins_centroid, pin:1296-1324): segment headed by pin q =
 // (pin q, centroid of its net); a 2-pin net has the single segment (pin 0, pin 1).
 __device__ __forceinline__ void centroid_route(const Dims& d, const RouteScratch& rs, int lane,
-                                               int n_pins, int& crossings, double& wl) {
+                                               int n_pins, int n_nets, int& crossings, double& wl) {
   for (int q = lane; q < n_pins; q += 32) {
     const int net = rs.net[q];
     const int lo = rs.net_off[net], cnt = rs.net_off[net + 1] - lo;
     double x2 = 0.0, y2 = 0.0, len = 0.0;  // + 0.0 leaves the running sum unchanged
     uint2 box = no_box();
     if (cnt != 2 || q == lo) {
-      if (cnt == 2) { x2 = (double)rs.px[q + 1]; y2 = (double)rs.py[q + 1]; }
-      else { x2 = rs.cx[net]; y2 = rs.cy[net]; }
-      const double x1 = (double)rs.px[q], y1 = (double)rs.py[q];
-      box = make_box(x1, y1, x2, y2);
+      const int ix = rs.px[q], iy = rs.py[q];
+      if (cnt == 2) {
+        const int jx = rs.px[q + 1], jy = rs.py[q + 1];
+        x2 = (double)jx; y2 = (double)jy;
+        put_segment(rs, q, ix, iy, jx, jy, 1);
+        box = make_box(ix, iy, jx, jy);
+      } else {
+        x2 = rs.cx[net]; y2 = rs.cy[net];
+        if (cnt <= kMaxExactScale)
+          put_segment(rs, q, ix * cnt, iy * cnt, rs.nsum[2 * net], rs.nsum[2 * net + 1], cnt);
+        else
+          put_segment(rs, q, 0, 0, 0, 0, 0);  // coordinates would not fit 16 bits: float64 only
+        box = make_box(ix, iy, x2, y2);
+      }
+      const double x1 = (double)ix, y1 = (double)iy;
       len = norm2(x1 - x2, y1 - y2, d.norm_fma);
     }
     rs.x2[q] = x2; rs.y2[q] = y2; rs.box[q] = box; rs.dist[q] = len;
@@ -1147,17 +1259,12 @@ __device__ __forceinline__ void centroid_route(const Dims& d, const RouteScratch
 #ifdef PCB_EXP_NO_CROSS  // sensitivity experiment only (wrong rewards): how much of the interference is the crossing count?
   crossings = 0;
 #else
-  crossings = count_crossings(rs, lane, n_pins);
+  crossings = count_crossings(rs, lane, n_pins, n_nets);
 #endif
-  // find_wirelength (pin:741-759): the reference's sequential float64 sum, net by net.
-  // Every lane runs the same chain; the operands come from registers via shuffles so
-  // only the additions are dependent.
+  // find_wirelength (pin:741-759): the reference's sequential float64 sum, net by net (pins
+  // that head no segment hold 0.0).  Every lane runs the same chain over broadcast loads.
   double acc = 0.0;
-  for (int q0 = 0; q0 < n_pins; q0 += 32) {
-    const double mine = q0 + lane < n_pins ? rs.dist[q0 + lane] : 0.0;
-    const int m = n_pins - q0 < 32 ? n_pins - q0 : 32;
-    for (int q = 0; q < m; ++q) acc += __shfl_sync(kFull, mine, q);
-  }
+  for (int q = 0; q < n_pins; ++q) acc += rs.dist[q];
   wl = acc;
   __syncwarp();
 }
@@ -1453,7 +1560,7 @@ reward_kernel(const __grid_constant__ Params p) {
     int crossings = 0;
     double length = 0.0;
     if (!BEAM || d.reward_type == 0) {
-      centroid_route(d, rs, lane, n_pins, crossings, length);
+      centroid_route(d, rs, lane, n_pins, n_nets, crossings, length);
     } else if constexpr (BEAM) {
       // the paths were routed by beam_kernel (one thread per net) into the job record
       const uint16_t* jn = reinterpret_cast<const uint16_t*>(job + job_path_offset(d.max_pins));
@@ -1463,7 +1570,7 @@ reward_kernel(const __grid_constant__ Params p) {
       beam_route(d, rs, lane, n_pins, n_nets, crossings, length);
       if (d.reward_type == 2) {  // "both": fewer crossings wins, beam on ties (pin:643-661)
         int c2; double l2;
-        centroid_route(d, rs, lane, n_pins, c2, l2);
+        centroid_route(d, rs, lane, n_pins, n_nets, c2, l2);
         if (c2 < crossings) { crossings = c2; length = l2; }
       }
     }

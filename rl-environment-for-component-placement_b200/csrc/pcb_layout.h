@@ -95,9 +95,10 @@ struct Layout {
 PCB_HD constexpr int align16c(int v) { return (v + 15) & ~15; }
 PCB_HD constexpr int maxc(int a, int b) { return a > b ? a : b; }
 
-// terminal-reward scratch per warp: per-pin arrays + per-net arrays + pair queue
+// terminal-reward scratch per warp: per-pin arrays + per-net arrays + two pair queues
 PCB_HD constexpr int route_scratch_bytes(int max_pins, int K) {
-  return max_pins * (8 + 8 + 8 + 8 + 2 + 2 + 2 + 1) + K * (8 + 8 + 2 + 2) + 2 + kPairQueue * 4 + 64;
+  return max_pins * (8 + 8 + 8 + 8 + 8 + 2 + 2 + 2 + 1 + 1) + K * (8 + 8 + 8 + 2 + 2) + 2 +
+         2 * kPairQueue * 4 + 64;
 }
 
 // Pin env: the pin feature rows (C * P rows of 10 bytes) are staged in shared memory in passes

@@ -581,7 +581,7 @@ reward_list_kernel(const __grid_constant__ RewardListParams p) {
     int crossings = 0;
     double length = 0.0;
     if (!BEAM || d.reward_type == 0) {
-      centroid_route(d, rs, lane, n_pins, crossings, length);
+      centroid_route(d, rs, lane, n_pins, n_nets, crossings, length);
     } else if constexpr (BEAM) {
       // the paths were routed by beam_kernel (one thread per net) into the job record
       const uint16_t* jn = reinterpret_cast<const uint16_t*>(job + job_path_offset(d.max_pins));
@@ -591,7 +591,7 @@ reward_list_kernel(const __grid_constant__ RewardListParams p) {
       beam_route(d, rs, lane, n_pins, n_nets, crossings, length);
       if (d.reward_type == 2) {  // "both": fewer crossings wins, beam on ties (pin:643-661)
         int c2; double l2;
-        centroid_route(d, rs, lane, n_pins, c2, l2);
+        centroid_route(d, rs, lane, n_pins, n_nets, c2, l2);
         if (c2 < crossings) { crossings = c2; length = l2; }
       }
     }
