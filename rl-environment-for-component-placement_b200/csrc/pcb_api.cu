@@ -1539,7 +1539,7 @@ static int restore_result_halves(pcb_env_t* e, int n_steps, const double* d_rewa
   return 0;
 }
 
-constexpr int kHostChunk = 8;  // pcb_steps_host uploads the action rows in chunks of 8 steps
+constexpr int kHostChunk = 8;  // pcb_steps_host uploads the action rows in chunks of 8 steps (after the first row)
 
 static int ensure_host_staging(pcb_env_t* e, size_t steps) {
   if (steps <= e->hs_steps) return 0;
@@ -1595,7 +1595,9 @@ int pcb_steps_host(pcb_env_t* e, const int32_t* h_actions, int n_steps, int acti
   // Pin kinds: one step + one reward kernel per row.  The action rows travel on a copy
   // stream in chunks (the first step starts after the first chunk, not after all rows); the
   // results of step t leave on the stream its reward kernel ran on, while step t+1 runs.
-  const size_t chunks = (T + kHostChunk - 1) / kHostChunk;
+  // chunk 0 is the first row alone, so that the first step waits for one row, not for eight
+  auto chunk_begin = [](size_t c) { return c == 0 ? (size_t)0 : 1 + (c - 1) * (size_t)kHostChunk; };
+  const size_t chunks = 1 + (T - 1 + kHostChunk - 1) / kHostChunk;
   while (e->hs_events.size() < chunks) {
     cudaEvent_t ev = nullptr;
     CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -1604,15 +1606,16 @@ int pcb_steps_host(pcb_env_t* e, const int32_t* h_actions, int n_steps, int acti
   CU(cudaEventRecord(e->ev_host, st));           // the copy stream starts after the caller's work
   CU(cudaStreamWaitEvent(e->copy, e->ev_host, 0));
   for (size_t c = 0; c < chunks; ++c) {
-    const size_t t0 = c * kHostChunk, nt = std::min((size_t)kHostChunk, T - t0);
+    const size_t t0 = chunk_begin(c), nt = std::min(chunk_begin(c + 1), T) - t0;
     CU(cudaMemcpyAsync(e->hs_actions + t0 * per, h_actions + t0 * per, nt * per * sizeof(int32_t),
                        cudaMemcpyHostToDevice, e->copy));
     CU(cudaEventRecord(e->hs_events[c], e->copy));
   }
   const bool routes = e->d.kind >= 2;
   const bool overlap = routes && e->overlap;
+  size_t next_chunk = 0;
   for (size_t t = 0; t < T; ++t) {
-    if (t % kHostChunk == 0) CU(cudaStreamWaitEvent(st, e->hs_events[t / kHostChunk], 0));
+    if (t == chunk_begin(next_chunk)) CU(cudaStreamWaitEvent(st, e->hs_events[next_chunk++], 0));
     double* rrow = e->hs_reward + t * N;
     uint8_t* drow = e->hs_done + t * N;
     rc = step_impl(e, e->hs_actions + t * per, action_format, 0, nullptr, stream, overlap, rrow, drow);

@@ -657,3 +657,62 @@ def test_step_host_with_adjacent_result_buffers():
         f(t)
         assert np.array_equal(rew.numpy(), f.reward.numpy()) and np.array_equal(done.numpy(), f.done.numpy()), t
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("name", ["C", "E", "C_both"])
+def test_rollout_calls_reuse_the_actions_drawn_by_the_previous_call(name):
+    """The last step of a pcb_rollout_random call also draws the actions of the step after it and
+    the next call with the same seed starts from them instead of launching the stand-alone
+    sampler.  Per-step kernels (plain launches on the default stream): one launch fewer per
+    follow-up call, dropped by a reset / another seed / a step in between, and every
+    trajectory equal to a hand-written {sample; step} loop, which never takes that path."""
+    n = 150
+    a, b = make(name, n, seed=3, obs_ring=3, bank_size=4 * n), make(name, n, seed=3, obs_ring=3, bank_size=4 * n)
+    a.fused_rollout(False); b.fused_rollout(False)
+    a.reset(); b.reset()
+    width = a.spec.action_width
+
+    def by_hand(steps, seed, log=None):
+        for t in range(steps):
+            act = b.sample_random_actions(seed=seed)
+            if log is not None:
+                assert torch.equal(log[t], act), (name, t)
+            b.step(act)
+
+    def same(tag):
+        torch.cuda.synchronize()
+        assert np.array_equal(a.state_dict()["state"], b.state_dict()["state"]), (name, tag)
+        for k in a.obs_ring_tensors:
+            assert torch.equal(a.obs_ring_tensors[k], b.obs_ring_tensors[k]), (name, tag, k)
+        ra, rb = a.results(), b.results()
+        for k in ("reward", "done"):
+            assert torch.equal(ra[k], rb[k]), (name, tag, k)
+
+    def launches(fn):
+        l0 = a.launch_count
+        fn()
+        return a.launch_count - l0
+
+    first = launches(lambda: a.rollout_random(7, seed=5))
+    by_hand(7, 5); same("first call")
+    again = launches(lambda: a.rollout_random(7, seed=5))
+    by_hand(7, 5); same("second call")
+    assert again == first - 1                      # no sampler launch
+    log = torch.zeros((9, n, width), dtype=torch.int32, device="cuda")
+    logged = launches(lambda: a.rollout_random(9, seed=5, actions_log=log))
+    by_hand(9, 5, log); same("logged call")        # first row of the log = the kept actions
+    assert logged * 7 == again * 9
+    other = launches(lambda: a.rollout_random(7, seed=6))
+    by_hand(7, 6); same("another seed")
+    assert other == first                          # sampled again
+    a.reset(mask=(torch.arange(n, device="cuda") % 3 == 0))
+    b.reset(mask=(torch.arange(n, device="cuda") % 3 == 0))
+    after_reset = launches(lambda: a.rollout_random(7, seed=6))
+    by_hand(7, 6); same("after a partial reset")
+    assert after_reset == first
+    act = a.sample_random_actions(seed=9)
+    a.step(act); b.step(b.sample_random_actions(seed=9))
+    after_step = launches(lambda: a.rollout_random(7, seed=6))
+    by_hand(7, 6); same("after a plain step")
+    assert after_step == first
+    a.close(); b.close()
