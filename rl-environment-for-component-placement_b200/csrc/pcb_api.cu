@@ -117,6 +117,7 @@ struct pcb_env {
   uint8_t* jobs;       // routing jobs (pin kinds)
   uint32_t* job_count; // [2]
   size_t reward_smem;
+  bool reward_half;      // centroid reward, max_pins <= 32: reward_half_kernel (two jobs per warp)
   int reward_grid;       // reward_kernel grid when it runs alone
   int reward_grid_side;  // ... when it overlaps the next step kernel (pcb_rollout_random)
   cudaStream_t side;     // stream of the overlapped reward kernels
@@ -291,7 +292,10 @@ int launch(pcb_env* e, KernelId id, const Params& p, cudaStream_t st, int reward
   if (id == K_TERM) {
     dim3 rgrid(reward_grid > 0 ? reward_grid : e->reward_grid);
     if (e->d.reward_type == PCB_REWARD_CENTROID) {
-      reward_kernel<false><<<rgrid, block, e->reward_smem, st>>>(p);
+      if (e->reward_half)  // two jobs per warp: half the CTAs for the same jobs per group
+        reward_half_kernel<<<dim3((rgrid.x + kGroups - 1) / kGroups), block, e->reward_smem * kGroups, st>>>(p);
+      else
+        reward_kernel<false><<<rgrid, block, e->reward_smem, st>>>(p);
     } else {
       beam_kernel<<<rgrid, 128, 0, st>>>(p);  // thread per (job, net); paths go into the jobs
       e->launches += 1;
@@ -702,11 +706,17 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
     }
   }
   e->jobs = nullptr; e->job_count = nullptr; e->reward_smem = 0; e->reward_grid = 1; e->reward_grid_side = 1;
+  e->reward_half = false;
   e->side = nullptr; e->rew_pending[0] = e->rew_pending[1] = false; e->overlap = PCB_OVERLAP_REWARD != 0;
   for (int i = 0; i < 2; ++i) { e->ev_step[i] = nullptr; e->ev_rew[i] = nullptr; }
   if (d.kind >= 2) {
     e->reward_smem = (size_t)((route_scratch_bytes(d.max_pins, d.K) + 15) & ~15) * kWarpsPerCta;
     TRY(set_smem(reward_kernel<false>, e->reward_smem));
+    e->reward_half = PCB_REWARD_HALF != 0 && d.reward_type == PCB_REWARD_CENTROID && d.max_pins <= 32;
+    if (e->reward_half) {
+      TRY(set_smem(reward_half_kernel, e->reward_smem * kGroups));
+      TRY(set_smem(reward_list_half_kernel, e->reward_smem * kGroups));
+    }
     TRY(set_smem(reward_kernel<true>, e->reward_smem));
     TRY(set_smem(reward_list_kernel<false>, e->reward_smem));
     TRY(set_smem(reward_list_kernel<true>, e->reward_smem));
@@ -1289,7 +1299,11 @@ static int rollout_pin_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* 
       CU(cudaStreamWaitEvent(e->side, e->ev_step[buf], 0));
     }
     if (e->d.reward_type == PCB_REWARD_CENTROID) {
-      reward_list_kernel<false><<<std::max(1, want_ctas), kWarpsPerCta * 32, e->reward_smem, rst>>>(r);
+      if (e->reward_half)
+        reward_list_half_kernel<<<std::max(1, (want_ctas + kGroups - 1) / kGroups), kWarpsPerCta * 32,
+                                  e->reward_smem * kGroups, rst>>>(r);
+      else
+        reward_list_kernel<false><<<std::max(1, want_ctas), kWarpsPerCta * 32, e->reward_smem, rst>>>(r);
     } else {
       // beam_kernel over the list: it reads its job count at job_count[step_no & 3]
       Params bp;

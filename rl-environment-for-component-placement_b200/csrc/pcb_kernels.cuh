@@ -1658,4 +1658,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) sample_kernel(const Params 
 }
 
 }  // namespace pcb
+#include "pcb_reward_half.cuh"
+
 #endif

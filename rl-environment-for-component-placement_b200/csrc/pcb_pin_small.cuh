@@ -623,5 +623,52 @@ reward_list_kernel(const __grid_constant__ RewardListParams p) {
   }
 }
 
+// reward_list_kernel<false> with two (four) jobs per warp: pcb_reward_half.cuh
+__global__ void __launch_bounds__(kWarpsPerCta * 32, PCB_REWARD_MIN_BLOCKS)
+reward_list_half_kernel(const __grid_constant__ RewardListParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const Dims& d = p.d;
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  const int gl = lane & (kG - 1), grp = lane / kG, gbase = lane & ~(kG - 1);
+  const uint32_t gw = blockIdx.x * kWarpsPerCta + wic, nw = gridDim.x * kWarpsPerCta;
+  const uint32_t total = *p.job_total;
+  const uint32_t count = total < p.job_cap ? total : p.job_cap;
+  const int scr_bytes = (route_scratch_bytes(d.max_pins, d.K) + 15) & ~15;
+  RouteScratch rs = route_scratch(smem + (size_t)(wic * kGroups + grp) * scr_bytes, d.max_pins, d.K);
+  const uint32_t N = (uint32_t)p.n_envs;
+  for (uint32_t j0 = gw * kGroups; j0 < count; j0 += nw * kGroups) {
+    const uint32_t j = j0 + (uint32_t)grp;
+    const bool has = j < count;
+    const uint8_t* job = p.jobs + (size_t)(has ? j : j0) * job_stride(d.max_pins, d.K);
+    const RouteJob hdr = *reinterpret_cast<const RouteJob*>(job);
+    prefetch_job(d, p.jobs, j + nw * kGroups, count, gl);
+    const GroupReward r = reward_of_group(d, rs, job, hdr, has, gl, gbase);
+    if (has && gl == 0) {
+      const uint32_t env = hdr.env;
+      const int t = (int)hdr.pad;
+      const double ret = hdr.ep_return + r.reward;
+      if (p.reward_log) p.reward_log[(size_t)t * N + env] = r.reward;
+      if (t >= p.final_from) {
+        const bool odd = ((p.step_no + (uint64_t)t) & 1ull) != 0;
+        const uint32_t he = odd ? N + env : env;
+        const size_t hoff = odd ? (size_t)p.res_stride : 0;
+        *reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(p.base.reward + env) + hoff) = r.reward;
+        p.base.wl[he] = r.wl; p.base.ni[he] = r.ni;
+        p.base.ep_return[he] = ret;
+        p.base.ep_length[he] = (int32_t)hdr.ep_len;
+      }
+      if (hdr.count_stats) {
+        double* st = p.stats + (size_t)(env & (kStatSlots - 1)) * 8;
+        atomicAdd(st + 0, 1.0);
+        atomicAdd(st + 1, ret);
+        atomicAdd(st + 2, (double)hdr.ep_len);
+        atomicAdd(st + 3, r.wl);
+        atomicAdd(st + 4, r.ni);
+      }
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace pcb
 #endif
