@@ -118,6 +118,7 @@ struct pcb_env {
   uint32_t* job_count; // [2]
   size_t reward_smem;
   bool reward_half;      // centroid reward, max_pins <= 32: reward_half_kernel (two jobs per warp)
+  int list_group;        // lanes per job of reward_list_half_kernel: 16 or 8 (reward_list_group_lanes)
   int reward_grid;       // reward_kernel grid when it runs alone
   int reward_grid_side;  // ... when it overlaps the next step kernel (pcb_rollout_random)
   cudaStream_t side;     // stream of the overlapped reward kernels
@@ -207,6 +208,7 @@ enum KernelId { K_STEP, K_TERM, K_RESET, K_SAMPLE };
 // outstanding timing events are bounded: past kMaxTimed pairs the finished ones are folded
 // into running totals (a caller that enables timing and never polls does not grow the list)
 constexpr size_t kMaxTimed = 4096;
+constexpr int kStepGroups = 32 / kStepGroupLanes;  // jobs per warp of reward_half_kernel
 int fold_timed(pcb_env* e) {
   for (auto& t : e->timed) {
     CU(cudaEventSynchronize(t.b));
@@ -293,7 +295,8 @@ int launch(pcb_env* e, KernelId id, const Params& p, cudaStream_t st, int reward
     dim3 rgrid(reward_grid > 0 ? reward_grid : e->reward_grid);
     if (e->d.reward_type == PCB_REWARD_CENTROID) {
       if (e->reward_half)  // two jobs per warp: half the CTAs for the same jobs per group
-        reward_half_kernel<<<dim3((rgrid.x + kGroups - 1) / kGroups), block, e->reward_smem * kGroups, st>>>(p);
+        reward_half_kernel<kStepGroupLanes><<<dim3((rgrid.x + kStepGroups - 1) / kStepGroups), block,
+                                              e->reward_smem * kStepGroups, st>>>(p);
       else
         reward_kernel<false><<<rgrid, block, e->reward_smem, st>>>(p);
     } else {
@@ -706,7 +709,7 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
     }
   }
   e->jobs = nullptr; e->job_count = nullptr; e->reward_smem = 0; e->reward_grid = 1; e->reward_grid_side = 1;
-  e->reward_half = false;
+  e->reward_half = false; e->list_group = 16;
   e->side = nullptr; e->rew_pending[0] = e->rew_pending[1] = false; e->overlap = PCB_OVERLAP_REWARD != 0;
   for (int i = 0; i < 2; ++i) { e->ev_step[i] = nullptr; e->ev_rew[i] = nullptr; }
   if (d.kind >= 2) {
@@ -714,8 +717,10 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
     TRY(set_smem(reward_kernel<false>, e->reward_smem));
     e->reward_half = PCB_REWARD_HALF != 0 && d.reward_type == PCB_REWARD_CENTROID && d.max_pins <= 32;
     if (e->reward_half) {
-      TRY(set_smem(reward_half_kernel, e->reward_smem * kGroups));
-      TRY(set_smem(reward_list_half_kernel, e->reward_smem * kGroups));
+      e->list_group = reward_list_group_lanes(d.max_pins);
+      TRY(set_smem(reward_half_kernel<kStepGroupLanes>, e->reward_smem * kStepGroups));
+      TRY(set_smem(reward_list_half_kernel<16>, e->reward_smem * 2));
+      TRY(set_smem(reward_list_half_kernel<8>, e->reward_smem * 4));
     }
     TRY(set_smem(reward_kernel<true>, e->reward_smem));
     TRY(set_smem(reward_list_kernel<false>, e->reward_smem));
@@ -1299,10 +1304,14 @@ static int rollout_pin_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* 
       CU(cudaStreamWaitEvent(e->side, e->ev_step[buf], 0));
     }
     if (e->d.reward_type == PCB_REWARD_CENTROID) {
-      if (e->reward_half)
-        reward_list_half_kernel<<<std::max(1, (want_ctas + kGroups - 1) / kGroups), kWarpsPerCta * 32,
-                                  e->reward_smem * kGroups, rst>>>(r);
-      else
+      if (e->reward_half) {
+        const int groups = 32 / e->list_group;
+        const int ctas = std::max(1, (want_ctas + groups - 1) / groups);
+        if (e->list_group == 8)
+          reward_list_half_kernel<8><<<ctas, kWarpsPerCta * 32, e->reward_smem * groups, rst>>>(r);
+        else
+          reward_list_half_kernel<16><<<ctas, kWarpsPerCta * 32, e->reward_smem * groups, rst>>>(r);
+      } else
         reward_list_kernel<false><<<std::max(1, want_ctas), kWarpsPerCta * 32, e->reward_smem, rst>>>(r);
     } else {
       // beam_kernel over the list: it reads its job count at job_count[step_no & 3]

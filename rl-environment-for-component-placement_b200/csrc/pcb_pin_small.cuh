@@ -624,8 +624,10 @@ reward_list_kernel(const __grid_constant__ RewardListParams p) {
 }
 
 // reward_list_kernel<false> with two (four) jobs per warp: pcb_reward_half.cuh
+template <int kG>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, PCB_REWARD_MIN_BLOCKS)
 reward_list_half_kernel(const __grid_constant__ RewardListParams p) {
+  constexpr int kGroups = 32 / kG;
   extern __shared__ __align__(16) uint8_t smem[];
   const Dims& d = p.d;
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
@@ -641,8 +643,8 @@ reward_list_half_kernel(const __grid_constant__ RewardListParams p) {
     const bool has = j < count;
     const uint8_t* job = p.jobs + (size_t)(has ? j : j0) * job_stride(d.max_pins, d.K);
     const RouteJob hdr = *reinterpret_cast<const RouteJob*>(job);
-    prefetch_job(d, p.jobs, j + nw * kGroups, count, gl);
-    const GroupReward r = reward_of_group(d, rs, job, hdr, has, gl, gbase);
+    prefetch_job<kG>(d, p.jobs, j + nw * kGroups, count, gl);
+    const GroupReward r = reward_of_group<kG>(d, rs, job, hdr, has, gl, gbase);
     if (has && gl == 0) {
       const uint32_t env = hdr.env;
       const int t = (int)hdr.pad;

@@ -17,16 +17,28 @@
 
 namespace pcb {
 
+// Every routine below is a template on kG = lanes per job: 16 (two jobs per warp) or 8 (four).
+// The per-step kernel always runs 16 (with 8 lanes a job of a 32 x 32 board takes longer than the
+// step kernel it hides behind); the job-list kernel of the multi-step path runs 8 on boards whose
+// jobs have few pins (reward_list_group_lanes).
 #ifndef PCB_REWARD_GROUP
 #define PCB_REWARD_GROUP 16
 #endif
-constexpr int kG = PCB_REWARD_GROUP;  // lanes per job: 16 (two jobs per warp) or 8 (four)
-static_assert(kG == 16 || kG == 8, "PCB_REWARD_GROUP");
-constexpr int kGroups = 32 / kG;
+#ifndef PCB_REWARD_LIST_GROUP_SMALL
+#define PCB_REWARD_LIST_GROUP_SMALL 8
+#endif
+constexpr int kStepGroupLanes = PCB_REWARD_GROUP;
+static_assert(kStepGroupLanes == 16 || kStepGroupLanes == 8, "PCB_REWARD_GROUP");
+// lanes per job of reward_list_half_kernel: a job has about half of max_pins pins
+inline int reward_list_group_lanes(int max_pins) {
+  return max_pins <= 20 ? PCB_REWARD_LIST_GROUP_SMALL : 16;
+}
 
+template <int kG>
 __device__ __forceinline__ unsigned grp_ballot(bool pred, int gbase) {
   return (__ballot_sync(kFull, pred) >> gbase) & ((1u << kG) - 1u);
 }
+template <int kG>
 __device__ __forceinline__ int grp_sum(int v) {
   if (kG > 8) v += __shfl_xor_sync(kFull, v, 8);
   v += __shfl_xor_sync(kFull, v, 4);
@@ -36,6 +48,7 @@ __device__ __forceinline__ int grp_sum(int v) {
 }
 
 // route_prepare for a group; np_u / nn_u = the larger pin / net count of the two jobs
+template <int kG>
 __device__ __forceinline__ void route_prepare_half(const JobPin* pins, const RouteScratch& rs, int gl,
                                                    int n_pins, int n_nets, int np_u, int nn_u) {
   for (int q0 = 0; q0 < np_u; q0 += kG) {
@@ -67,6 +80,7 @@ __device__ __forceinline__ void route_prepare_half(const JobPin* pins, const Rou
 
 // count_crossings for a group of 16 lanes (see count_crossings: dense pair enumeration, integer
 // box filter, exact integer test, float64 formula for what that leaves undecided)
+template <int kG>
 __device__ __forceinline__ int count_crossings_half(const RouteScratch& rs, int gl, int gbase,
                                                     int n_nets) {
   int cnt = 0, qn = 0, hn = 0;
@@ -85,7 +99,7 @@ __device__ __forceinline__ int count_crossings_half(const RouteScratch& rs, int 
       r = segments_cross_int(rs, pr);
     }
     cnt += r & 1;
-    const unsigned hb = grp_ballot(r == 2, gbase);
+    const unsigned hb = grp_ballot<kG>(r == 2, gbase);
     if (r == 2) rs.hqueue[hn + __popc(hb & below)] = pr;
     hn += __popc(hb);
     __syncwarp();
@@ -113,7 +127,7 @@ __device__ __forceinline__ int count_crossings_half(const RouteScratch& rs, int 
       const int q = __float2int_rz(((float)i + 0.5f) * inv);
       const int s = i - q * first, t = live ? first + q : 0;
       const bool pass = boxes_touch(rs.box[t], rs.box[s]) && live;
-      const unsigned pb = grp_ballot(pass, gbase);
+      const unsigned pb = grp_ballot<kG>(pass, gbase);
       if (pass) rs.queue[qn + __popc(pb & below)] = ((uint32_t)s << 16) | (uint32_t)t;
       qn += __popc(pb);
       __syncwarp();
@@ -133,10 +147,11 @@ __device__ __forceinline__ int count_crossings_half(const RouteScratch& rs, int 
   }
   if (gl < hn) cnt += heavy(rs.hqueue[gl]);
   __syncwarp();
-  return grp_sum(cnt);
+  return grp_sum<kG>(cnt);
 }
 
 // centroid_route for a group
+template <int kG>
 __device__ __forceinline__ void centroid_route_half(const Dims& d, const RouteScratch& rs, int gl,
                                                     int gbase, int n_pins, int n_nets, int np_u,
                                                     int& crossings, double& wl) {
@@ -168,7 +183,7 @@ __device__ __forceinline__ void centroid_route_half(const Dims& d, const RouteSc
     }
   }
   __syncwarp();
-  crossings = count_crossings_half(rs, gl, gbase, n_nets);
+  crossings = count_crossings_half<kG>(rs, gl, gbase, n_nets);
   // find_wirelength (pin:741-759): sequential float64 sum over the pins of this group's job
   double acc = 0.0;
   for (int q = 0; q < np_u; ++q)
@@ -181,15 +196,16 @@ struct GroupReward { double reward, wl, ni; };
 
 // terminal reward of this group's job (has == false: the group sits the round out but takes part
 // in every warp-wide operation)
+template <int kG>
 __device__ __forceinline__ GroupReward reward_of_group(const Dims& d, const RouteScratch& rs,
                                                        const uint8_t* job, const RouteJob& hdr, bool has,
                                                        int gl, int gbase) {
   const int n_pins = has ? hdr.n_pins : 0, n_nets = has ? hdr.n_nets : 0;
   const int np_u = __reduce_max_sync(kFull, n_pins), nn_u = __reduce_max_sync(kFull, n_nets);
-  route_prepare_half(reinterpret_cast<const JobPin*>(job + 32), rs, gl, n_pins, n_nets, np_u, nn_u);
+  route_prepare_half<kG>(reinterpret_cast<const JobPin*>(job + 32), rs, gl, n_pins, n_nets, np_u, nn_u);
   int crossings = 0;
   double length = 0.0;
-  centroid_route_half(d, rs, gl, gbase, n_pins, n_nets, np_u, crossings, length);
+  centroid_route_half<kG>(d, rs, gl, gbase, n_pins, n_nets, np_u, crossings, length);
   GroupReward r;
   r.wl = length / d.wl_norm;             // pin:921 / 940 / 959-961
   r.ni = (double)crossings / d.ni_norm;  // pin:922-924
@@ -198,6 +214,7 @@ __device__ __forceinline__ GroupReward reward_of_group(const Dims& d, const Rout
 }
 
 // the record of a group's next job: on its way to L1 while the current one is computed
+template <int kG>
 __device__ __forceinline__ void prefetch_job(const Dims& d, const uint8_t* jobs, uint32_t jn, uint32_t count,
                                              int gl) {
   const int line = gl * 128;
@@ -205,8 +222,10 @@ __device__ __forceinline__ void prefetch_job(const Dims& d, const uint8_t* jobs,
     asm volatile("prefetch.global.L1 [%0];" ::"l"(jobs + (size_t)jn * job_stride(d.max_pins, d.K) + line));
 }
 
+template <int kG>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, PCB_REWARD_MIN_BLOCKS)
 reward_half_kernel(const __grid_constant__ Params p) {
+  constexpr int kGroups = 32 / kG;
   extern __shared__ __align__(16) uint8_t smem[];
   const Dims& d = p.d;
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
@@ -222,8 +241,8 @@ reward_half_kernel(const __grid_constant__ Params p) {
     const bool has = j < count;
     const uint8_t* job = p.jobs + (size_t)(has ? j : j0) * job_stride(d.max_pins, d.K);
     const RouteJob hdr = *reinterpret_cast<const RouteJob*>(job);
-    prefetch_job(d, p.jobs, j + nw * kGroups, count, gl);
-    const GroupReward r = reward_of_group(d, rs, job, hdr, has, gl, gbase);
+    prefetch_job<kG>(d, p.jobs, j + nw * kGroups, count, gl);
+    const GroupReward r = reward_of_group<kG>(d, rs, job, hdr, has, gl, gbase);
     if (has && gl == 0) {
       const int env = (int)hdr.env;
       const double ret = hdr.ep_return + r.reward;
