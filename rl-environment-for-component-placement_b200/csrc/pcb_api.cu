@@ -974,7 +974,7 @@ static int rollout_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_ac
 static int step_impl(pcb_env_t* e, const int32_t* d_actions, int action_format, uint64_t seed,
                      int32_t* d_next_actions, void* stream, bool overlap,
                      double* reward_row = nullptr, uint8_t* done_row = nullptr,
-                     const uint64_t* step_base = nullptr) {
+                     const uint64_t* step_base = nullptr, bool last_of_call = false) {
   int rc = ready(e);
   if (rc) return rc;
   if (!d_actions) return fail(PCB_ERR_INVALID, "d_actions is NULL");
@@ -1009,7 +1009,8 @@ static int step_impl(pcb_env_t* e, const int32_t* d_actions, int action_format, 
     } else {
       CU(cudaEventRecord(e->ev_step[par], st));
       CU(cudaStreamWaitEvent(e->side, e->ev_step[par], 0));
-      rc = launch(e, K_TERM, p, e->side, e->reward_grid_side);
+      // no step kernel runs beside the reward kernel of a call's last step: full grid
+      rc = launch(e, K_TERM, p, e->side, last_of_call ? e->reward_grid : e->reward_grid_side);
       if (rc) return rc;
       CU(cudaEventRecord(e->ev_rew[par], e->side));
       e->rew_pending[par] = true;
@@ -1406,7 +1407,8 @@ static int graph_capture(pcb_env_t* e, uint64_t seed, int L, cudaStream_t st, bo
   int32_t* cur = e->d_actions;
   for (int t = 0; t < L && rc == 0; ++t) {
     int32_t* nxt = cur == e->d_actions ? e->d_actions2 : e->d_actions;
-    rc = step_impl(e, cur, PCB_ACTION_TUPLE, seed, nxt, st, overlap, nullptr, nullptr, e->d_step_base);
+    // (the graph joins its last reward kernel before it ends: nothing runs beside that one)
+    rc = step_impl(e, cur, PCB_ACTION_TUPLE, seed, nxt, st, overlap, nullptr, nullptr, e->d_step_base, t + 1 == L);
     cur = nxt;
   }
   if (rc == 0) rc = join_rewards(e, st);
@@ -1518,7 +1520,8 @@ int pcb_rollout_random_logged(pcb_env_t* e, uint64_t seed, int n_steps, int32_t*
         nxt = cur == e->d_actions ? e->d_actions2 : e->d_actions;
       int rc2 = step_impl(e, cur, PCB_ACTION_TUPLE, seed, nxt, stream, e->overlap,
                           d_reward_log ? d_reward_log + (size_t)done * N : nullptr,
-                          d_done_log ? d_done_log + (size_t)done * N : nullptr);
+                          d_done_log ? d_done_log + (size_t)done * N : nullptr, nullptr,
+                          last_of_call && t + 1 == count);
       if (rc2) return rc2;
       cur = nxt;
       n_steps -= 1;
@@ -1641,20 +1644,24 @@ int pcb_steps_host(pcb_env_t* e, const int32_t* h_actions, int n_steps, int acti
     if (t == chunk_begin(next_chunk)) CU(cudaStreamWaitEvent(st, e->hs_events[next_chunk++], 0));
     double* rrow = e->hs_reward + t * N;
     uint8_t* drow = e->hs_done + t * N;
-    rc = step_impl(e, e->hs_actions + t * per, action_format, 0, nullptr, stream, overlap, rrow, drow);
+    rc = step_impl(e, e->hs_actions + t * per, action_format, 0, nullptr, stream, overlap, rrow, drow,
+                   nullptr, t + 1 == T);
     if (rc) return rc;
     cudaStream_t out = overlap ? e->side : st;   // the stream on which row t becomes final
     CU(cudaMemcpyAsync(h_reward + t * N, rrow, N * sizeof(double), cudaMemcpyDeviceToHost, out));
     CU(cudaMemcpyAsync(h_done + t * N, drow, N, cudaMemcpyDeviceToHost, out));
   }
   if (overlap) {
-    rc = join_rewards(e, st);
+    rc = join_rewards(e, st);                    // the reward kernels ...
     if (rc) return rc;
+  }
+  // (on `stream`, beside the last rows' copies to the host on the side stream)
+  rc = restore_result_halves(e, n_steps, e->hs_reward, e->hs_done, st);
+  if (rc) return rc;
+  if (overlap) {
     CU(cudaEventRecord(e->ev_host, e->side));    // ... and the copies queued behind them
     CU(cudaStreamWaitEvent(st, e->ev_host, 0));
   }
-  rc = restore_result_halves(e, n_steps, e->hs_reward, e->hs_done, st);
-  if (rc) return rc;
   CU(cudaStreamSynchronize(st));
   return 0;
 }
