@@ -119,6 +119,7 @@ struct pcb_env {
   size_t reward_smem;
   bool reward_half;      // centroid reward, max_pins <= 32: reward_half_kernel (two jobs per warp)
   int list_group;        // lanes per job of reward_list_half_kernel: 16 or 8 (reward_list_group_lanes)
+  int step_group;        // ... of reward_half_kernel (reward_step_group_lanes)
   int reward_grid;       // reward_kernel grid when it runs alone
   int reward_grid_side;  // ... when it overlaps the next step kernel (pcb_rollout_random)
   cudaStream_t side;     // stream of the overlapped reward kernels
@@ -208,7 +209,6 @@ enum KernelId { K_STEP, K_TERM, K_RESET, K_SAMPLE };
 // outstanding timing events are bounded: past kMaxTimed pairs the finished ones are folded
 // into running totals (a caller that enables timing and never polls does not grow the list)
 constexpr size_t kMaxTimed = 4096;
-constexpr int kStepGroups = 32 / kStepGroupLanes;  // jobs per warp of reward_half_kernel
 int fold_timed(pcb_env* e) {
   for (auto& t : e->timed) {
     CU(cudaEventSynchronize(t.b));
@@ -294,10 +294,12 @@ int launch(pcb_env* e, KernelId id, const Params& p, cudaStream_t st, int reward
   if (id == K_TERM) {
     dim3 rgrid(reward_grid > 0 ? reward_grid : e->reward_grid);
     if (e->d.reward_type == PCB_REWARD_CENTROID) {
-      if (e->reward_half)  // two jobs per warp: half the CTAs for the same jobs per group
-        reward_half_kernel<kStepGroupLanes><<<dim3((rgrid.x + kStepGroups - 1) / kStepGroups), block,
-                                              e->reward_smem * kStepGroups, st>>>(p);
-      else
+      if (e->reward_half) {  // two (four) jobs per warp: as many CTAs fewer for the same jobs per group
+        const int groups = 32 / e->step_group;
+        const dim3 hgrid((rgrid.x + groups - 1) / groups);
+        if (e->step_group == 8) reward_half_kernel<8><<<hgrid, block, e->reward_smem * groups, st>>>(p);
+        else reward_half_kernel<16><<<hgrid, block, e->reward_smem * groups, st>>>(p);
+      } else
         reward_kernel<false><<<rgrid, block, e->reward_smem, st>>>(p);
     } else {
       beam_kernel<<<rgrid, 128, 0, st>>>(p);  // thread per (job, net); paths go into the jobs
@@ -709,7 +711,7 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
     }
   }
   e->jobs = nullptr; e->job_count = nullptr; e->reward_smem = 0; e->reward_grid = 1; e->reward_grid_side = 1;
-  e->reward_half = false; e->list_group = 16;
+  e->reward_half = false; e->list_group = 16; e->step_group = 16;
   e->side = nullptr; e->rew_pending[0] = e->rew_pending[1] = false; e->overlap = PCB_OVERLAP_REWARD != 0;
   for (int i = 0; i < 2; ++i) { e->ev_step[i] = nullptr; e->ev_rew[i] = nullptr; }
   if (d.kind >= 2) {
@@ -718,7 +720,9 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
     e->reward_half = PCB_REWARD_HALF != 0 && d.reward_type == PCB_REWARD_CENTROID && d.max_pins <= 32;
     if (e->reward_half) {
       e->list_group = reward_list_group_lanes(d.max_pins);
-      TRY(set_smem(reward_half_kernel<kStepGroupLanes>, e->reward_smem * kStepGroups));
+      e->step_group = reward_step_group_lanes(d.kind);
+      TRY(set_smem(reward_half_kernel<16>, e->reward_smem * 2));
+      TRY(set_smem(reward_half_kernel<8>, e->reward_smem * 4));
       TRY(set_smem(reward_list_half_kernel<16>, e->reward_smem * 2));
       TRY(set_smem(reward_list_half_kernel<8>, e->reward_smem * 4));
     }

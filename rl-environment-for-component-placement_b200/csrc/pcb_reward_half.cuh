@@ -18,17 +18,26 @@
 namespace pcb {
 
 // Every routine below is a template on kG = lanes per job: 16 (two jobs per warp) or 8 (four).
-// The per-step kernel always runs 16 (with 8 lanes a job of a 32 x 32 board takes longer than the
-// step kernel it hides behind); the job-list kernel of the multi-step path runs 8 on boards whose
-// jobs have few pins (reward_list_group_lanes).
+// The per-step kernel runs 16: with 8 lanes the jobs of a step of 32 x 32 boards take longer than
+// the pin env's step kernel they hide behind (C 0.850 -> 0.775); beside the spatial env's step
+// kernel, which lasts twice as long, 8 lanes give +1.4 % on the device-timed rollout but -3.4 %
+// through pcb_steps_host, where each reward kernel is followed by its copies to the host
+// (profiles/r2h_reward_group_spatial_ab.log), so that stays 16 as well.  The job-list kernel of
+// the multi-step path runs 8 on boards whose jobs have few pins (reward_list_group_lanes).
 #ifndef PCB_REWARD_GROUP
 #define PCB_REWARD_GROUP 16
+#endif
+#ifndef PCB_REWARD_GROUP_SPATIAL
+#define PCB_REWARD_GROUP_SPATIAL 16
 #endif
 #ifndef PCB_REWARD_LIST_GROUP_SMALL
 #define PCB_REWARD_LIST_GROUP_SMALL 8
 #endif
-constexpr int kStepGroupLanes = PCB_REWARD_GROUP;
-static_assert(kStepGroupLanes == 16 || kStepGroupLanes == 8, "PCB_REWARD_GROUP");
+static_assert(PCB_REWARD_GROUP == 16 || PCB_REWARD_GROUP == 8, "PCB_REWARD_GROUP");
+static_assert(PCB_REWARD_GROUP_SPATIAL == 16 || PCB_REWARD_GROUP_SPATIAL == 8, "PCB_REWARD_GROUP_SPATIAL");
+static_assert(PCB_REWARD_LIST_GROUP_SMALL == 16 || PCB_REWARD_LIST_GROUP_SMALL == 8, "PCB_REWARD_LIST_GROUP_SMALL");
+// lanes per job of reward_half_kernel (kind 3 = the spatial pin env)
+inline int reward_step_group_lanes(int kind) { return kind == 3 ? PCB_REWARD_GROUP_SPATIAL : PCB_REWARD_GROUP; }
 // lanes per job of reward_list_half_kernel: a job has about half of max_pins pins
 inline int reward_list_group_lanes(int max_pins) {
   return max_pins <= 20 ? PCB_REWARD_LIST_GROUP_SMALL : 16;
