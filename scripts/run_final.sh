@@ -10,9 +10,9 @@ timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench.json
 timeout 600 python bench.py --steps 128 --warmup 16 --no-cpu --no-secondary > gpurun_out/${TAG}_bench128.json 2> gpurun_out/${TAG}_bench128.err
 CMD="python bench.py --steps 8 --warmup 3 --no-cpu --no-secondary"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_l_$TAG.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"step_kernel|reward_kernel" -s 26 -c 4 -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_f_$TAG.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"step_kernel|reward_half_kernel|reward_kernel" -s 26 -c 4 -o gpurun_out/prof_$TAG $CMD > gpurun_out/ncu_f_$TAG.log 2>&1
 python scripts/ncu_summary.py gpurun_out/prof_$TAG.ncu-rep > gpurun_out/ncu_${TAG}_summary.txt 2>&1
-for K in step_kernel reward_kernel; do
+for K in step_kernel reward_half_kernel; do
   ncu -i gpurun_out/prof_$TAG.ncu-rep --page source --csv --print-source cuda,sass -k regex:$K -c 1 > gpurun_out/src_$TAG.csv 2>/dev/null
   python scripts/ncu_lines.py gpurun_out/src_$TAG.csv 60 > gpurun_out/ncu_${TAG}_${K}_lines.txt 2>&1
 done
