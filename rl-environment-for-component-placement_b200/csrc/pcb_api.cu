@@ -120,6 +120,7 @@ struct pcb_env {
   bool reward_half;      // centroid reward, max_pins <= 32: reward_half_kernel (two jobs per warp)
   int list_group;        // lanes per job of reward_list_half_kernel: 16 or 8 (reward_list_group_lanes)
   int step_group;        // ... of reward_half_kernel (reward_step_group_lanes)
+  bool list_half_beam;   // reward types beam / both, max_pins <= 32: reward_list_half_kernel<G, true>
   int reward_grid;       // reward_kernel grid when it runs alone
   int reward_grid_side;  // ... when it overlaps the next step kernel (pcb_rollout_random)
   cudaStream_t side;     // stream of the overlapped reward kernels
@@ -711,13 +712,20 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
     }
   }
   e->jobs = nullptr; e->job_count = nullptr; e->reward_smem = 0; e->reward_grid = 1; e->reward_grid_side = 1;
-  e->reward_half = false; e->list_group = 16; e->step_group = 16;
+  e->reward_half = false; e->list_group = 16; e->step_group = 16; e->list_half_beam = false;
   e->side = nullptr; e->rew_pending[0] = e->rew_pending[1] = false; e->overlap = PCB_OVERLAP_REWARD != 0;
   for (int i = 0; i < 2; ++i) { e->ev_step[i] = nullptr; e->ev_rew[i] = nullptr; }
   if (d.kind >= 2) {
     e->reward_smem = (size_t)((route_scratch_bytes(d.max_pins, d.K) + 15) & ~15) * kWarpsPerCta;
     TRY(set_smem(reward_kernel<false>, e->reward_smem));
     e->reward_half = PCB_REWARD_HALF != 0 && d.reward_type == PCB_REWARD_CENTROID && d.max_pins <= 32;
+    // reward types beam / both over the job list of the multi-step path: two (four) jobs per warp too
+    e->list_half_beam = PCB_REWARD_HALF != 0 && d.reward_type != PCB_REWARD_CENTROID && d.max_pins <= 32;
+    if (e->list_half_beam) {
+      e->list_group = reward_list_group_lanes(d.max_pins);
+      TRY((set_smem(reward_list_half_kernel<16, true>, e->reward_smem * 2)));
+      TRY((set_smem(reward_list_half_kernel<8, true>, e->reward_smem * 4)));
+    }
     if (e->reward_half) {
       e->list_group = reward_list_group_lanes(d.max_pins);
       e->step_group = reward_step_group_lanes(d.kind);
@@ -1326,7 +1334,15 @@ static int rollout_pin_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* 
       beam_kernel<<<std::max(1, want_ctas), 128, 0, rst>>>(bp);
       CU(cudaGetLastError());
       e->launches += 1;
-      reward_list_kernel<true><<<std::max(1, want_ctas), kWarpsPerCta * 32, e->reward_smem, rst>>>(r);
+      if (e->list_half_beam) {
+        const int groups = 32 / e->list_group;
+        const int ctas = std::max(1, (want_ctas + groups - 1) / groups);
+        if (e->list_group == 8)
+          reward_list_half_kernel<8, true><<<ctas, kWarpsPerCta * 32, e->reward_smem * groups, rst>>>(r);
+        else
+          reward_list_half_kernel<16, true><<<ctas, kWarpsPerCta * 32, e->reward_smem * groups, rst>>>(r);
+      } else
+        reward_list_kernel<true><<<std::max(1, want_ctas), kWarpsPerCta * 32, e->reward_smem, rst>>>(r);
     }
     CU(cudaGetLastError());
     if (overlap) {

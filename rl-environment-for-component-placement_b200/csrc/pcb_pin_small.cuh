@@ -623,8 +623,8 @@ reward_list_kernel(const __grid_constant__ RewardListParams p) {
   }
 }
 
-// reward_list_kernel<false> with two (four) jobs per warp: pcb_reward_half.cuh
-template <int kG>
+// reward_list_kernel with two (four) jobs per warp: pcb_reward_half.cuh
+template <int kG, bool BEAM = false>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, PCB_REWARD_MIN_BLOCKS)
 reward_list_half_kernel(const __grid_constant__ RewardListParams p) {
   constexpr int kGroups = 32 / kG;
@@ -644,7 +644,7 @@ reward_list_half_kernel(const __grid_constant__ RewardListParams p) {
     const uint8_t* job = p.jobs + (size_t)(has ? j : j0) * job_stride(d.max_pins, d.K);
     const RouteJob hdr = *reinterpret_cast<const RouteJob*>(job);
     prefetch_job<kG>(d, p.jobs, j + nw * kGroups, count, gl);
-    const GroupReward r = reward_of_group<kG>(d, rs, job, hdr, has, gl, gbase);
+    const GroupReward r = reward_of_group<kG, BEAM>(d, rs, job, hdr, has, gl, gbase);
     if (has && gl == 0) {
       const uint32_t env = hdr.env;
       const int t = (int)hdr.pad;

@@ -201,11 +201,52 @@ __device__ __forceinline__ void centroid_route_half(const Dims& d, const RouteSc
   __syncwarp();
 }
 
+// beam_route (pcb_beam.cuh) for a group: crossings + wirelength of the paths beam_kernel left in the
+// job record; the segment headed by pin q is (q, nxt[q])
+template <int kG>
+__device__ __forceinline__ void beam_route_half(const Dims& d, const RouteScratch& rs, int gl, int gbase,
+                                                int n_pins, int n_nets, int np_u, int& crossings,
+                                                double& wl) {
+  for (int q0 = 0; q0 < np_u; q0 += kG) {
+    const int q = q0 + gl;
+    if (q < n_pins) {
+      const int nx = rs.nxt[q];
+      double x2 = 0.0, y2 = 0.0, len = 0.0;
+      uint2 box = no_box();
+      if (nx != 0xFFFF) {
+        const int ix = rs.px[q], iy = rs.py[q], jx = rs.px[nx], jy = rs.py[nx];
+        x2 = (double)jx; y2 = (double)jy;
+        put_segment(rs, q, ix, iy, jx, jy, 1);
+        box = make_box(ix, iy, jx, jy);
+        len = norm2((double)ix - x2, (double)iy - y2, d.norm_fma);
+      }
+      rs.x2[q] = x2; rs.y2[q] = y2; rs.box[q] = box; rs.dist[q] = len;
+    }
+  }
+  __syncwarp();
+  crossings = count_crossings_half<kG>(rs, gl, gbase, n_nets);
+  // find_wirelength: nets in order, segments in path order, sequential float64 sum (the first lane
+  // of each group walks its job's paths)
+  double acc = 0.0;
+  if (gl == 0) {
+    for (int net = 0; net < n_nets; ++net) {
+      int q = rs.start[net];
+      while (rs.nxt[q] != 0xFFFF) {
+        acc += rs.dist[q];
+        q = rs.nxt[q];
+      }
+    }
+  }
+  wl = __shfl_sync(kFull, acc, gbase);
+  __syncwarp();
+}
+
 struct GroupReward { double reward, wl, ni; };
 
 // terminal reward of this group's job (has == false: the group sits the round out but takes part
-// in every warp-wide operation)
-template <int kG>
+// in every warp-wide operation).  BEAM: reward types "beam" / "both" as well, the paths routed by
+// beam_kernel are in the job record.
+template <int kG, bool BEAM = false>
 __device__ __forceinline__ GroupReward reward_of_group(const Dims& d, const RouteScratch& rs,
                                                        const uint8_t* job, const RouteJob& hdr, bool has,
                                                        int gl, int gbase) {
@@ -214,7 +255,20 @@ __device__ __forceinline__ GroupReward reward_of_group(const Dims& d, const Rout
   route_prepare_half<kG>(reinterpret_cast<const JobPin*>(job + 32), rs, gl, n_pins, n_nets, np_u, nn_u);
   int crossings = 0;
   double length = 0.0;
-  centroid_route_half<kG>(d, rs, gl, gbase, n_pins, n_nets, np_u, crossings, length);
+  if (!BEAM || d.reward_type == 0) {
+    centroid_route_half<kG>(d, rs, gl, gbase, n_pins, n_nets, np_u, crossings, length);
+  } else if constexpr (BEAM) {
+    const uint16_t* jn = reinterpret_cast<const uint16_t*>(job + job_path_offset(d.max_pins));
+    for (int q = gl; q < n_pins; q += kG) rs.nxt[q] = jn[q];
+    for (int k = gl; k < n_nets; k += kG) rs.start[k] = jn[d.max_pins + k];
+    __syncwarp();
+    beam_route_half<kG>(d, rs, gl, gbase, n_pins, n_nets, np_u, crossings, length);
+    if (d.reward_type == 2) {  // "both": fewer crossings wins, beam on ties (pin:643-661)
+      int c2; double l2;
+      centroid_route_half<kG>(d, rs, gl, gbase, n_pins, n_nets, np_u, c2, l2);
+      if (c2 < crossings) { crossings = c2; length = l2; }
+    }
+  }
   GroupReward r;
   r.wl = length / d.wl_norm;             // pin:921 / 940 / 959-961
   r.ni = (double)crossings / d.ni_norm;  // pin:922-924
