@@ -23,7 +23,8 @@ namespace pcb {
 // kernel, which lasts twice as long, 8 lanes give +1.4 % on the device-timed rollout but -3.4 %
 // through pcb_steps_host, where each reward kernel is followed by its copies to the host
 // (profiles/r2h_reward_group_spatial_ab.log), so that stays 16 as well.  The job-list kernel of
-// the multi-step path runs 8 on boards whose jobs have few pins (reward_list_group_lanes).
+// the multi-step path is bound by instruction issue, not by the latency of one job, and runs 8
+// (reward_list_group_lanes; profiles/r2h_reward_list_group8_ab.log).
 #ifndef PCB_REWARD_GROUP
 #define PCB_REWARD_GROUP 16
 #endif
@@ -38,9 +39,12 @@ static_assert(PCB_REWARD_GROUP_SPATIAL == 16 || PCB_REWARD_GROUP_SPATIAL == 8, "
 static_assert(PCB_REWARD_LIST_GROUP_SMALL == 16 || PCB_REWARD_LIST_GROUP_SMALL == 8, "PCB_REWARD_LIST_GROUP_SMALL");
 // lanes per job of reward_half_kernel (kind 3 = the spatial pin env)
 inline int reward_step_group_lanes(int kind) { return kind == 3 ? PCB_REWARD_GROUP_SPATIAL : PCB_REWARD_GROUP; }
-// lanes per job of reward_list_half_kernel: a job has about half of max_pins pins
+// lanes per job of reward_list_half_kernel
+#ifndef PCB_REWARD_LIST_SMALL_MAX_PINS
+#define PCB_REWARD_LIST_SMALL_MAX_PINS 32
+#endif
 inline int reward_list_group_lanes(int max_pins) {
-  return max_pins <= 20 ? PCB_REWARD_LIST_GROUP_SMALL : 16;
+  return max_pins <= PCB_REWARD_LIST_SMALL_MAX_PINS ? PCB_REWARD_LIST_GROUP_SMALL : 16;
 }
 
 template <int kG>
