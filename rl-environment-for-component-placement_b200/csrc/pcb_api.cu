@@ -132,6 +132,8 @@ struct pcb_env {
   // pin / pin-spatial env, H, W <= 32: rollout_pin_kernel (pcb_pin_small.cuh) -- many steps
   // per launch, 32/LPE envs per warp, terminal rewards from a job list afterwards
   bool fused_pin, fused_pin_ok;
+  int list_side_mult;  // list_steps: CTAs per SM (in units of 8 one-job warps) of the side kernels
+  bool list_steps;  // multi-step pin path with per-step kernels filling the job list (list_steps_chunk)
   size_t pin_smem;       // dynamic shared memory per CTA (4 warps)
   uint8_t* pin_jobs[2];  // job lists of two launches in flight, pin_job_steps * N records each
   uint32_t* pin_job_total[2];
@@ -202,6 +204,7 @@ Params make_params(const pcb_env* e, bool for_reset = false) {
   p.ratio_lut = e->ratio_lut;
   p.jobs = e->jobs ? e->jobs + (size_t)parity * e->n_envs * job_stride(e->d.max_pins, e->d.K) : nullptr;
   p.job_count = e->job_count;
+  p.job_slot_mask = 3; p.job_t = 0;
   return p;
 }
 
@@ -209,6 +212,12 @@ enum KernelId { K_STEP, K_TERM, K_RESET, K_SAMPLE };
 
 // outstanding timing events are bounded: past kMaxTimed pairs the finished ones are folded
 // into running totals (a caller that enables timing and never polls does not grow the list)
+#ifndef PCB_LIST_SIDE_MULT
+#define PCB_LIST_SIDE_MULT 16
+#endif
+#ifndef PCB_LIST_STEPS
+#define PCB_LIST_STEPS 1  // reward types beam / both at large batches: list_steps_chunk
+#endif
 constexpr size_t kMaxTimed = 4096;
 int fold_timed(pcb_env* e) {
   for (auto& t : e->timed) {
@@ -671,7 +680,7 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
       else TRY((set_smem_shape<1, uint32_t, DynShape>(e->smem_bytes)));
   }
   e->fused = d.kind <= 1 && !e->wide;
-  e->fused_pin = false; e->fused_pin_ok = false; e->pin_smem = 0;
+  e->fused_pin = false; e->fused_pin_ok = false; e->pin_smem = 0; e->list_steps = false;
   e->pin_jobs[0] = e->pin_jobs[1] = nullptr;
   e->pin_job_total[0] = e->pin_job_total[1] = nullptr; e->pin_job_steps = 0;
   e->sms = 148;
@@ -698,10 +707,22 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
     // path (one side stream, ~100 us of latency-bound work per step); over the job list of a
     // 64-step launch the same kernels run with 64x the parallelism: C "both" at 65 536 envs
     // 4.0e8 -> 5.5e8 env-steps/s, "beam" 4.6e8 -> 6.0e8, at 4 096 envs 7.5e7 -> 4.6e8.
+    // list_steps_chunk (step_kernel per step as the PRODUCER of the job list) is off by default:
+    // measured slower than rollout_pin_kernel at every side-grid size (C "both" at 65 536 envs
+    // 5.56e8 against 5.69e8, "beam" 6.11e8 against 6.27e8; profiles/r2h_list_steps_producer.log)
+    // -- over a job list the router and the reward kernel are bound by instruction issue, so
+    // they take their time from whichever stepper runs beside them.  PCB_LIST_STEPS_MIN_ENVS
+    // turns it on from that batch size (tests, experiments).
+    int list_min = 0x7fffffff;
+    if (const char* f = getenv("PCB_LIST_STEPS_MIN_ENVS")) list_min = atoi(f);
     if (d.reward_type != PCB_REWARD_CENTROID) max_envs = 0x7fffffff;
     if (const char* f = getenv("PCB_PIN_FUSED_MAX_ENVS")) max_envs = atoi(f);
     e->fused_pin_ok = true;
     e->fused_pin = lpe < 32 || num_envs <= max_envs;
+    e->list_side_mult = PCB_LIST_SIDE_MULT;
+    if (const char* f = getenv("PCB_LIST_SIDE_MULT")) e->list_side_mult = std::max(1, atoi(f));  // experiments
+    e->list_steps = PCB_LIST_STEPS != 0 && lpe == 32 && num_envs >= list_min && e->fused_pin &&
+                    d.reward_type != PCB_REWARD_CENTROID;
     const PinSmem L = pin_smem_layout(d.kind, d.C, d.L.P, d.max_pins, d.H, d.W, d.K, d.mh, d.mw);
     e->pin_smem = (size_t)kLutBytes + (size_t)L.total * kWarpsPerCta * (32 / lpe);
     if (e->pin_smem > 200 * 1024) { e->fused_pin_ok = false; e->fused_pin = false; }
@@ -1237,6 +1258,48 @@ static int rollout_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* d_ac
   return 0;
 }
 
+static int restore_result_halves(pcb_env_t* e, int n_steps, const double* d_reward_log,
+                                 const uint8_t* d_done_log, cudaStream_t st);
+// One chunk of the multi-step pin path produced by per-step kernels: nt launches of step_kernel
+// that leave their routing jobs in the chunk's job list (Params::job_slot_mask = 0, job_t = step
+// of the chunk) instead of one launch of rollout_pin_kernel.  Used for the reward types beam /
+// both at batch sizes where one warp per env and a launch per step is the faster stepper (the
+// router and the reward kernel then run over the list beside the next chunk, as for
+// rollout_pin_kernel).  `cur` holds the actions of the next step of the random policy.
+static int list_steps_chunk(pcb_env_t* e, uint64_t seed, int t0, int nt, int n_steps, int buf,
+                            int32_t* d_actions_log, double* d_reward_log, uint8_t* d_done_log,
+                            cudaStream_t st, const int32_t* d_actions, int action_format, size_t per,
+                            int32_t** cur) {
+  const size_t N = (size_t)e->n_envs;
+  for (int t = 0; t < nt; ++t) {
+    const int g = t0 + t;  // step of the call
+    e->slice = (e->slice + 1) % e->ring;
+    Params p = make_params(e);
+    int32_t* nxt = nullptr;
+    if (d_actions) {
+      p.actions = d_actions + (size_t)g * per;
+      p.action_format = action_format;
+    } else {
+      p.actions = *cur;
+      p.action_format = PCB_ACTION_TUPLE;
+      if (g + 1 < n_steps)
+        nxt = d_actions_log ? d_actions_log + (size_t)(g + 1) * N * 3
+                            : (*cur == e->d_actions ? e->d_actions2 : e->d_actions);
+    }
+    p.seed = seed;
+    p.actions_out = nxt;
+    if (d_reward_log) p.out.reward = d_reward_log + (size_t)g * N;
+    if (d_done_log) p.out.done = d_done_log + (size_t)g * N;
+    p.jobs = e->pin_jobs[buf]; p.job_count = e->pin_job_total[buf];
+    p.job_slot_mask = 0; p.job_t = (uint32_t)t;
+    int rc = launch(e, K_STEP, p, st);
+    if (rc) return rc;
+    e->step_no += 1;
+    if (nxt) *cur = nxt;
+  }
+  return 0;
+}
+
 // the pin env: n_steps in launches of up to pin_job_steps steps of rollout_pin_kernel, each
 // followed by reward_list_kernel over the routing jobs it left -- on the side stream, so the
 // rewards of launch k are computed while launch k+1 steps (two job lists alternate).  Cutting a
@@ -1277,6 +1340,13 @@ static int rollout_pin_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* 
     CU(cudaEventCreate(&b));
     CU(cudaEventRecord(a, st));
   }
+  int32_t* cur = nullptr;  // list_steps: the actions of the next step of the random policy
+  if (e->list_steps && !d_actions) {
+    cur = d_actions_log ? d_actions_log : e->d_actions;
+    int rc = pcb_sample_random_actions(e, seed, cur, st);
+    if (rc) return rc;
+  }
+  e->pend_actions = nullptr;
   int k = 0;
   for (int t0 = 0; t0 < n_steps; t0 += chunk, ++k) {
     const int nt = std::min(chunk, n_steps - t0), buf = k & 1;
@@ -1300,7 +1370,16 @@ static int rollout_pin_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* 
     p.n_envs = e->n_envs; p.n_steps = nt; p.ring = e->ring; p.slice0 = e->slice;
     p.jobs = e->pin_jobs[buf]; p.job_total = e->pin_job_total[buf];
     p.job_cap = (uint32_t)std::min<size_t>((size_t)e->pin_job_steps * N, 0xffffffffu);
-    int rc = pin_dispatch(e, false, st, p);
+    int rc;
+    if (e->list_steps) {
+      const uint64_t step0 = e->step_no;
+      const int slice0 = e->slice;
+      rc = list_steps_chunk(e, seed, t0, nt, n_steps, buf, d_actions_log, d_reward_log, d_done_log, st,
+                            d_actions, action_format, per, &cur);
+      e->step_no = step0; e->slice = slice0;  // advanced below, as for rollout_pin_kernel
+    } else {
+      rc = pin_dispatch(e, false, st, p);
+    }
     if (rc) return rc;
     CU(cudaGetLastError());
     RewardListParams r;
@@ -1309,8 +1388,10 @@ static int rollout_pin_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* 
     r.jobs = e->pin_jobs[buf]; r.job_total = e->pin_job_total[buf]; r.job_cap = p.job_cap;
     r.reward_log = p.reward_log; r.step_no = e->step_no; r.stats = e->stats;
     r.final_from = std::max(0, n_steps - 2 - t0);  // beyond nt when the call goes on after this launch
+    // (list_steps: the router and the reward kernel share the SMs with the step kernels of the
+    // next chunk, like the per-step reward kernel does: a small persistent grid)
     const int want_ctas = (int)std::min<size_t>(((size_t)nt * N + kWarpsPerCta - 1) / kWarpsPerCta,
-                                                (size_t)e->sms * PCB_REWARD_GRID_MULT);
+                                                (size_t)e->sms * (e->list_steps ? e->list_side_mult : PCB_REWARD_GRID_MULT));
     cudaStream_t rst = overlap ? e->side : st;
     if (overlap) {
       CU(cudaEventRecord(e->ev_step[buf], st));
@@ -1349,12 +1430,17 @@ static int rollout_pin_fused(pcb_env_t* e, uint64_t seed, int n_steps, int32_t* 
       CU(cudaEventRecord(e->ev_rew[buf], e->side));
       e->rew_pending[buf] = true;
     }
-    e->launches += 2;
+    e->launches += e->list_steps ? 1 : 2;  // (launch() counted the step kernels)
     e->slice = (e->slice + nt) % e->ring;
     e->step_no += (uint64_t)nt;
   }
   int rc = join_rewards(e, st);
   if (rc) return rc;
+  // step_kernel writes a step's reward / done either into the log rows or into the result halves
+  if (e->list_steps && (d_reward_log || d_done_log)) {
+    rc = restore_result_halves(e, n_steps, d_reward_log, d_done_log, st);
+    if (rc) return rc;
+  }
   if (e->timing) {
     CU(cudaEventRecord(b, st));
     CU(cudaEventSynchronize(b));

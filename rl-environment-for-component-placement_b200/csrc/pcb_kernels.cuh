@@ -1289,13 +1289,13 @@ __device__ __forceinline__ void finish_episode(const S& sh, const Params& p, Env
     // all components placed: find_reward needs the routes -> leave the pin positions
     const int n_pins = e.hdr->n_pins;
     uint32_t idx = 0;
-    if (lane == 0) idx = atomicAdd(p.job_count + (p.step_no & 3), 1u);
+    if (lane == 0) idx = atomicAdd(p.job_count + (p.step_no & p.job_slot_mask), 1u);
     idx = __shfl_sync(kFull, idx, 0);
     uint8_t* job = p.jobs + (size_t)idx * job_stride(sh.max_pins(), sh.K());
     if (lane == 0) {
       RouteJob j;
       j.env = (uint32_t)env; j.n_pins = (uint16_t)n_pins; j.n_nets = e.hdr->n_nets;
-      j.count_stats = first_report ? 1 : 0; j.ep_len = e.hdr->ep_len; j.pad = 0;
+      j.count_stats = first_report ? 1 : 0; j.ep_len = e.hdr->ep_len; j.pad = p.job_t;
       j.ep_return = e.dyn->ep_return; j.pad2 = 0.0;
       *reinterpret_cast<RouteJob*>(job) = j;
     }

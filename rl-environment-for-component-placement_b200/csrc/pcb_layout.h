@@ -226,6 +226,10 @@ struct Params {
   int reset_first;
   uint8_t* jobs;        // [N][job_stride] routing jobs of the current step
   uint32_t* job_count;  // [4] job counters, ring indexed by step number
+  // step_kernel leaves its routing jobs at jobs[atomicAdd(job_count + (step_no & job_slot_mask))]
+  // with RouteJob::pad = job_t.  Per-step mode: mask 3 (the ring of counters), job_t 0.  List mode
+  // (the job list of a multi-step launch, filled by per-step kernels): mask 0, job_t = step of the launch.
+  uint32_t job_slot_mask, job_t;
   double* stats;      // [kStatSlots][8]
   uint64_t seed;
   uint64_t step_no;

@@ -716,3 +716,66 @@ def test_rollout_calls_reuse_the_actions_drawn_by_the_previous_call(name):
     by_hand(7, 6); same("after a plain step")
     assert after_step == first
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("name", ["C_both", "C_beam", "D_both"])
+@pytest.mark.parametrize("autoreset", [True, False])
+def test_list_steps_producer_equals_per_step(name, autoreset, monkeypatch):
+    """Reward types beam / both at large batches: per-step kernels fill the job list of a chunk,
+    router + reward kernel run over the list (list_steps_chunk, pcb_api.cu).  Forced here at a small
+    batch (PCB_LIST_STEPS_MIN_ENVS) and compared with the plain per-step path: observation slices,
+    logged actions / rewards / dones, state records, result tensors, statistics, and the caller's
+    actions through pcb_steps_host."""
+    cfg = CONFIGS[name]
+    if cfg["type"] not in ("rectangle_pin", "rectangle_spatial_pin") or cfg["height"] <= 16:
+        pytest.skip("boards of at most 16 rows always take rollout_pin_kernel")
+    n, T = 203, 41
+    monkeypatch.setenv("PCB_LIST_STEPS_MIN_ENVS", "1")
+    a = make(name, n, seed=11, obs_ring=T + 1, bank_size=5 * n, autoreset=autoreset)
+    monkeypatch.delenv("PCB_LIST_STEPS_MIN_ENVS")
+    b = make(name, n, seed=11, obs_ring=T + 1, bank_size=5 * n, autoreset=autoreset)
+    assert a.fused_rollout(True)
+    b.fused_rollout(False)
+    a.reset(); b.reset()
+    l0 = a.launch_count
+    logs = []
+    for e in (a, b):
+        al = torch.zeros((T, n, 3), dtype=torch.int32, device="cuda")
+        rl = torch.full((T, n), -7.0, dtype=torch.float64, device="cuda")
+        dl = torch.zeros((T, n), dtype=torch.uint8, device="cuda")
+        e.rollout_random(T, seed=3, actions_log=al, reward_log=rl, done_log=dl)
+        logs.append((al, rl, dl))
+    torch.cuda.synchronize()
+    # sampler + T step kernels + router + reward list kernel: the producer really ran per step
+    assert a.launch_count - l0 == T + 3, a.launch_count - l0
+    for x, y, what in zip(logs[0], logs[1], ("actions", "reward", "done")):
+        assert torch.equal(x, y), (name, what, (x != y).nonzero()[:5].tolist())
+    assert int(logs[0][2].sum()) > 0
+
+    def same(tag):
+        torch.cuda.synchronize()
+        for k in a.obs_ring_tensors:
+            assert torch.equal(a.obs_ring_tensors[k], b.obs_ring_tensors[k]), (name, tag, k)
+        assert np.array_equal(a.state_dict()["state"], b.state_dict()["state"]), (name, tag)
+        ra, rb = a.results(), b.results()
+        done = ra["done"].bool()
+        assert torch.equal(ra["done"], rb["done"]) and torch.equal(ra["reward"], rb["reward"]), (name, tag)
+        for k in ("wirelength", "num_intersections", "episode_return", "episode_length"):
+            assert torch.equal(ra[k][done], rb[k][done]), (name, tag, k)
+        sa, sb = a.episode_stats(), b.episode_stats()
+        for k in sa:
+            assert sa[k] == sb[k] if k in ("episodes", "steps", "sum_length") else np.isclose(sa[k], sb[k], rtol=1e-12), (name, tag, k)
+
+    same("logged")
+    for e in (a, b):                      # no logs, a length that needs several chunks
+        e.rollout_random(150, seed=4)
+        e.step(e.sample_random_actions(seed=9))   # a per-step call in between shares the state
+        e.rollout_random(7, seed=5)
+    same("plain")
+    acts = logs[0][0][:9].cpu().pin_memory()
+    Ra, Da = torch.zeros((9, n), dtype=torch.float64), torch.zeros((9, n), dtype=torch.uint8)
+    Rb, Db = torch.zeros((9, n), dtype=torch.float64), torch.zeros((9, n), dtype=torch.uint8)
+    a.steps_host(acts, Ra, Da); b.steps_host(acts, Rb, Db)
+    assert torch.equal(Ra, Rb) and torch.equal(Da, Db), name
+    same("given actions")
+    a.close(); b.close()
