@@ -305,7 +305,7 @@ def measure(args, ctx, name, N, main):
     # with 5 slices), so there the ring keeps every observation of the timed rollout -- what a
     # rollout collector needs anyway -- as long as that stays below 48 GB.
     slice_bytes = N * ALGO_BYTES[name]
-    ring = max(OBS_RING, -(-300_000_000 // slice_bytes))
+    ring = max(int(os.environ.get("PCB_BENCH_RING", OBS_RING)), -(-300_000_000 // slice_bytes))  # (env: experiments)
     pinless = cfg["type"] in ("square", "rectangle")
     if pinless and not args.no_fused:
         ring = max(ring, min(K + 1, 48_000_000_000 // slice_bytes))
