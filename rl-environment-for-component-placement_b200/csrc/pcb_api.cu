@@ -133,6 +133,7 @@ struct pcb_env {
   // per launch, 32/LPE envs per warp, terminal rewards from a job list afterwards
   bool fused_pin, fused_pin_ok;
   int list_side_mult;  // list_steps: CTAs per SM (in units of 8 one-job warps) of the side kernels
+  bool state_stream;  // Params::state_stream: the state records are larger than kStateStreamBytes
   bool list_steps;  // multi-step pin path with per-step kernels filling the job list (list_steps_chunk)
   size_t pin_smem;       // dynamic shared memory per CTA (4 warps)
   uint8_t* pin_jobs[2];  // job lists of two launches in flight, pin_job_steps * N records each
@@ -205,6 +206,7 @@ Params make_params(const pcb_env* e, bool for_reset = false) {
   p.jobs = e->jobs ? e->jobs + (size_t)parity * e->n_envs * job_stride(e->d.max_pins, e->d.K) : nullptr;
   p.job_count = e->job_count;
   p.job_slot_mask = 3; p.job_t = 0;
+  p.state_stream = e->state_stream ? 1u : 0u;
   return p;
 }
 
@@ -219,6 +221,7 @@ enum KernelId { K_STEP, K_TERM, K_RESET, K_SAMPLE };
 #define PCB_LIST_STEPS 1  // reward types beam / both at large batches: list_steps_chunk
 #endif
 constexpr size_t kMaxTimed = 4096;
+constexpr size_t kStateStreamBytes = 96u << 20;  // state records above this: streaming loads / stores
 int fold_timed(pcb_env* e) {
   for (auto& t : e->timed) {
     CU(cudaEventSynchronize(t.b));
@@ -781,6 +784,12 @@ int pcb_create(const pcb_config_t* cfg, int device, int num_envs, pcb_env_t** ou
   const size_t N = (size_t)num_envs, R = (size_t)e->ring;
   const int64_t n64 = num_envs, r64 = e->ring;
   TRY(dev_alloc(e, &e->state, N * d.L.st_stride));
+  // State records of 195 MB (E, 131 072 envs) never survive in the 126 MB L2 from one step to the
+  // next; loaded and stored with the streaming policy they leave it to the observation stores:
+  // E 1.947e8 -> 2.008e8 env-steps/s.  Records that mostly fit are better left alone (C, 24 MB:
+  // 7.27e8 -> 6.96e8 with streaming; D neutral) -- profiles/r2h_state_streaming_ab.log.
+  e->state_stream = e->wide && (size_t)N * d.L.st_stride > kStateStreamBytes;
+  if (const char* f = getenv("PCB_STATE_STREAM")) e->state_stream = atoi(f) != 0;  // experiments
   TRY(dev_alloc(e, &e->stats, kStatSlots * 8 * sizeof(double)));
   TRY(dev_alloc(e, &e->d_actions, N * 3 * sizeof(int32_t)));
   TRY(dev_alloc(e, &e->d_actions2, N * 3 * sizeof(int32_t)));

@@ -230,8 +230,10 @@ __device__ __forceinline__ uint64_t l2_evict_last_policy() {
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
-__device__ __forceinline__ uint4 ld_state(const void* p) {
-#if PCB_OPT_STATE_L2
+__device__ __forceinline__ uint4 ld_state(const void* p, bool stream) {
+  // stream: evict-first like the observation stores (Params::state_stream)
+  if (PCB_OPT_STATE_L2 == 2 || stream) return __ldcs(reinterpret_cast<const uint4*>(p));
+#if PCB_OPT_STATE_L2 == 1
   uint4 v;
   asm volatile("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(l2_evict_last_policy()));
@@ -240,8 +242,9 @@ __device__ __forceinline__ uint4 ld_state(const void* p) {
   return *reinterpret_cast<const uint4*>(p);
 #endif
 }
-__device__ __forceinline__ void st_state(void* p, uint4 v) {
-#if PCB_OPT_STATE_L2
+__device__ __forceinline__ void st_state(void* p, uint4 v, bool stream) {
+  if (PCB_OPT_STATE_L2 == 2 || stream) { __stcs(reinterpret_cast<uint4*>(p), v); return; }
+#if PCB_OPT_STATE_L2 == 1
   asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;"
                :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(l2_evict_last_policy()) : "memory");
 #else
@@ -249,10 +252,10 @@ __device__ __forceinline__ void st_state(void* p, uint4 v) {
 #endif
 }
 // shared -> global copy of a state record
-__device__ __forceinline__ void store_state(void* gdst, const void* ssrc, int nbytes, int lane) {
+__device__ __forceinline__ void store_state(void* gdst, const void* ssrc, int nbytes, int lane, bool stream) {
   const uint4* s4 = reinterpret_cast<const uint4*>(ssrc);
   uint4* d = reinterpret_cast<uint4*>(gdst);
-  for (int i = lane; i < (nbytes >> 4); i += 32) st_state(d + i, s4[i]);
+  for (int i = lane; i < (nbytes >> 4); i += 32) st_state(d + i, s4[i], stream);
 }
 
 // ---------------------------------------------------------------------------
@@ -1322,7 +1325,7 @@ __device__ __forceinline__ void finish_episode(const S& sh, const Params& p, Env
   if (!d.autoreset) {
     if (lane == 0 && first_report) {
       e.hdr->flags |= kFlagFinished;
-      st_state(gstate, *reinterpret_cast<const uint4*>(e.sm));
+      st_state(gstate, *reinterpret_cast<const uint4*>(e.sm), (RPL == 2 && p.state_stream != 0));
     }
     return;
   }
@@ -1336,7 +1339,7 @@ __device__ __forceinline__ void finish_episode(const S& sh, const Params& p, Env
 #pragma unroll
   for (int k = 0; k < RPL; ++k) occ[k] = T(0);
   next_masks<RPL, T, S>(sh, d, e, occ, 0, e.hdr->n_comp, lane, m0, m1);
-  store_state(gstate, e.sm, sh.st_stride(), lane);
+  store_state(gstate, e.sm, sh.st_stride(), lane, (RPL == 2 && p.state_stream != 0));
   write_obs<RPL, T, S>(sh, p, e, env, lane, occ, m0, m1);
   if (p.actions_out)
     sample_action<RPL, T, S>(sh, m0, m1, p.seed, env, policy_step(p) + 1, lane, p.actions_out);
@@ -1379,7 +1382,7 @@ __device__ __forceinline__ void step_env(const S& sh, const Params& p, Env<T>& e
   uint8_t* gstate = p.state + (size_t)env * sh.st_stride();
   if (lane < n16) reinterpret_cast<uint4*>(e.sm)[lane] = st0;
   for (int i = 32 + lane; i < n16; i += 32)
-    reinterpret_cast<uint4*>(e.sm)[i] = ld_state(reinterpret_cast<const uint4*>(gstate) + i);
+    reinterpret_cast<uint4*>(e.sm)[i] = ld_state(reinterpret_cast<const uint4*>(gstate) + i, (RPL == 2 && p.state_stream != 0));
   __syncwarp();
 
   T occ[RPL];
@@ -1462,9 +1465,9 @@ __device__ __forceinline__ void step_env(const S& sh, const Params& p, Env<T>& e
   if (!restart) {  // a restarting env overwrites its state below
     uint4* g4 = reinterpret_cast<uint4*>(gstate);
     const uint4* s4 = reinterpret_cast<const uint4*>(e.sm);
-    if (lane < 2) st_state(g4 + lane, s4[lane]);
+    if (lane < 2) st_state(g4 + lane, s4[lane], (RPL == 2 && p.state_stream != 0));
     if (valid)
-      for (int i = 2 + lane; i < (sh.st_stride() >> 4); i += 32) st_state(g4 + i, s4[i]);
+      for (int i = 2 + lane; i < (sh.st_stride() >> 4); i += 32) st_state(g4 + i, s4[i], (RPL == 2 && p.state_stream != 0));
   }
 
   if (!restart) {
@@ -1498,7 +1501,7 @@ step_kernel(const Params p) {
   build_expand_lut(smem);
   for (int env = blockIdx.x * kWarpsPerCta + wic; env < p.n_envs; env += gridDim.x * kWarpsPerCta) {
     uint4 st0 = make_uint4(0, 0, 0, 0);
-    if (lane < n16) st0 = ld_state(reinterpret_cast<const uint4*>(p.state + (size_t)env * sh.st_stride()) + lane);
+    if (lane < n16) st0 = ld_state(reinterpret_cast<const uint4*>(p.state + (size_t)env * sh.st_stride()) + lane, (RPL == 2 && p.state_stream != 0));
     int o, x, y;
     load_action(sh, p, env, o, x, y);
     step_env<RPL, T, S>(sh, p, e, env, lane, st0, o, x, y);
@@ -1523,7 +1526,7 @@ step_kernel(const Params p) {
   }
 #endif
   uint4 st0 = make_uint4(0, 0, 0, 0);
-  if (lane < n16) st0 = ld_state(reinterpret_cast<const uint4*>(p.state + (size_t)(live ? env : 0) * sh.st_stride()) + lane);
+  if (lane < n16) st0 = ld_state(reinterpret_cast<const uint4*>(p.state + (size_t)(live ? env : 0) * sh.st_stride()) + lane, (RPL == 2 && p.state_stream != 0));
   int o = 0, x = 0, y = 0;
   if (live) load_action(sh, p, env, o, x, y);
   expand_lut_store(smem, lut_part);
@@ -1624,7 +1627,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) reset_kernel(const Params p
 #pragma unroll
   for (int k = 0; k < RPL; ++k) occ[k] = T(0);
   next_masks<RPL, T, S>(sh, d, e, occ, 0, e.hdr->n_comp, lane, m0, m1);
-  store_state(gstate, e.sm, sh.st_stride(), lane);
+  store_state(gstate, e.sm, sh.st_stride(), lane, (RPL == 2 && p.state_stream != 0));
   write_obs<RPL, T, S>(sh, p, e, env, lane, occ, m0, m1);
   if (lane == 0) {
     p.out.done[env] = 0;

@@ -230,6 +230,11 @@ struct Params {
   // with RouteJob::pad = job_t.  Per-step mode: mask 3 (the ring of counters), job_t 0.  List mode
   // (the job list of a multi-step launch, filled by per-step kernels): mask 0, job_t = step of the launch.
   uint32_t job_slot_mask, job_t;
+  // the state records do not fit in L2 beside the observation stream (large batches of large
+  // boards): load / store them with the streaming policy, so that they leave L2 to the stores.
+  // Honoured by the kernels of boards wider than 32 only (RPL == 2): on the others the extra
+  // branch cost 0.9 % on config C, and their records reach that size only beyond 256 K envs.
+  uint32_t state_stream;
   double* stats;      // [kStatSlots][8]
   uint64_t seed;
   uint64_t step_no;
