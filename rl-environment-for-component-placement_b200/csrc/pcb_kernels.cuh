@@ -232,7 +232,7 @@ __device__ __forceinline__ uint64_t l2_evict_last_policy() {
 }
 __device__ __forceinline__ uint4 ld_state(const void* p, bool stream) {
   // stream: evict-first like the observation stores (Params::state_stream)
-  if (PCB_OPT_STATE_L2 == 2 || stream) return __ldcs(reinterpret_cast<const uint4*>(p));
+  if (PCB_OPT_STATE_L2 == 2 || PCB_OPT_STATE_L2 == 3 || stream) return __ldcs(reinterpret_cast<const uint4*>(p));  // (3 / 4: loads / stores only, experiments)
 #if PCB_OPT_STATE_L2 == 1
   uint4 v;
   asm volatile("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
@@ -243,7 +243,7 @@ __device__ __forceinline__ uint4 ld_state(const void* p, bool stream) {
 #endif
 }
 __device__ __forceinline__ void st_state(void* p, uint4 v, bool stream) {
-  if (PCB_OPT_STATE_L2 == 2 || stream) { __stcs(reinterpret_cast<uint4*>(p), v); return; }
+  if (PCB_OPT_STATE_L2 == 2 || PCB_OPT_STATE_L2 == 4 || stream) { __stcs(reinterpret_cast<uint4*>(p), v); return; }
 #if PCB_OPT_STATE_L2 == 1
   asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;"
                :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(l2_evict_last_policy()) : "memory");
